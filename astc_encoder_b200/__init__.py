@@ -1,0 +1,369 @@
+"""astc_encoder_b200 -- B200-native ASTC block encoder (sm_100a).
+
+Python host side over the C ABI in ``include/astc_b200.h`` (loaded with ctypes
+from the in-tree ``libastc_b200.so``).  The names mirror the reference's
+host interface so call sites read the same:
+
+    encode_option      astc_encode.h:14-28
+    encode_astc()      astc_encode.h:87     (device texture -> device block buffer, async)
+    read_gpu()         astc_save.h:34       (download + sync)
+    save_astc()        astc_save.h:52       (16-byte header + blocks)
+    load_tex()         main.cpp:19          (decode + vertical flip + RGBA8 + upload)
+
+PyTorch is used only as plumbing (device memory, streams, torch.distributed).
+There is no CPU encode path: if the CUDA library is missing or no GPU is
+visible, the compute entry points raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from pathlib import Path
+from typing import Optional, Sequence
+
+import numpy as np
+
+__all__ = [
+    "encode_option", "AstcError", "lib", "block_dim", "block_counts", "output_size", "band",
+    "encode_astc", "encode_astc_host", "read_gpu", "save_astc", "load_astc", "load_image", "load_tex",
+    "decode_astc", "bise_encode", "Batch", "launch_count", "unorm_lut", "version",
+]
+
+_PKG = Path(__file__).resolve().parent
+_LIB_PATH = _PKG / "libastc_b200.so"
+
+BLOCK_BYTES = 16
+
+
+class AstcError(RuntimeError):
+    """A C-ABI call returned a negative astc_b200_status."""
+
+    def __init__(self, status: int, where: str):
+        l = lib()
+        detail = l.astc_b200_last_cuda_error().decode() if status in (-2, -3, -4) else ""
+        super().__init__(f"{where}: {l.astc_b200_strerror(status).decode()} ({status}) {detail}".strip())
+        self.status = status
+
+
+class _Option(C.Structure):
+    _fields_ = [("is4x4", C.c_uint8), ("is6x6", C.c_uint8), ("is_normal_map", C.c_uint8),
+                ("has_alpha", C.c_uint8), ("srgb", C.c_uint8), ("reserved", C.c_uint8 * 3)]
+
+
+class _Image(C.Structure):
+    _fields_ = [("d_rgba", C.c_void_p), ("d_blocks", C.c_void_p), ("pitch_bytes", C.c_size_t),
+                ("width", C.c_int32), ("height", C.c_int32)]
+
+
+@dataclass
+class encode_option:
+    """Same fields, order and defaults as the reference struct (astc_encode.h:14-28)."""
+    is4x4: bool = True
+    is6x6: bool = False
+    is_normal_map: bool = False
+    has_alpha: bool = False
+    srgb: bool = False
+
+    def _abi(self) -> _Option:
+        return _Option(int(self.is4x4), int(self.is6x6), int(self.is_normal_map),
+                       int(self.has_alpha), int(self.srgb))
+
+    @classmethod
+    def from_args(cls, args: Sequence[str]) -> "encode_option":
+        """parse_cmd (main.cpp:140-178): exact flag matches, unknown flags ignored."""
+        o = cls()
+        for a in args:
+            if a == "-4x4":
+                o.is4x4 = True
+            elif a == "-6x6":
+                o.is6x6 = True
+            elif a == "-norm":
+                o.is_normal_map = True
+            elif a == "-srgb":
+                o.srgb = True
+            elif a == "-alpha":
+                o.has_alpha = True
+        return o
+
+
+_lib: Optional[C.CDLL] = None
+
+# name -> (restype, argtypes); also the list tests check against include/astc_b200.h
+_SIGNATURES = {
+    "astc_b200_version": (C.c_char_p, []),
+    "astc_b200_strerror": (C.c_char_p, [C.c_int]),
+    "astc_b200_last_cuda_error": (C.c_char_p, []),
+    "astc_b200_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "astc_b200_set_device": (C.c_int, [C.c_int]),
+    "astc_b200_device_info": (C.c_int, [C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                        C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
+    "astc_b200_option_default": (None, [C.POINTER(_Option)]),
+    "astc_b200_block_dim": (C.c_int, [C.POINTER(_Option)]),
+    "astc_b200_block_counts": (C.c_int, [C.c_int, C.c_int, C.POINTER(_Option), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "astc_b200_output_size": (C.c_size_t, [C.c_int, C.c_int, C.POINTER(_Option)]),
+    "astc_b200_band": (C.c_int, [C.c_int, C.c_int, C.POINTER(_Option), C.c_int, C.c_int, C.POINTER(C.c_int),
+                                 C.POINTER(C.c_int), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "astc_b200_encode_device": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.POINTER(_Option), C.c_void_p, C.c_void_p]),
+    "astc_b200_encode_host": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.POINTER(_Option), C.c_void_p]),
+    "astc_b200_batch_create": (C.c_int, [C.POINTER(_Image), C.c_int, C.POINTER(_Option), C.POINTER(C.c_void_p)]),
+    "astc_b200_batch_encode": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "astc_b200_batch_total_blocks": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "astc_b200_batch_destroy": (None, [C.c_void_p]),
+    "astc_b200_launch_count": (C.c_uint64, []),
+    "astc_b200_bise_encode_device": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "astc_b200_quant_layout": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "astc_b200_ise_bitcount": (C.c_uint32, [C.c_uint32, C.c_int]),
+    "astc_b200_integer_from_trits": (C.c_int, [C.c_int] * 5),
+    "astc_b200_integer_from_quints": (C.c_int, [C.c_int] * 3),
+    "astc_b200_scramble": (C.c_int, [C.c_int, C.c_int]),
+    "astc_b200_blockmode": (C.c_uint32, [C.c_int]),
+    "astc_b200_unorm_lut": (C.c_int, [C.c_int, C.POINTER(C.c_float)]),
+    "astc_b200_decode_device": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "astc_b200_malloc_device": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
+    "astc_b200_free_device": (C.c_int, [C.c_void_p]),
+    "astc_b200_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
+    "astc_b200_host_free": (C.c_int, [C.c_void_p]),
+    "astc_b200_memcpy_h2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "astc_b200_memcpy_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "astc_b200_memcpy2d_h2d": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p]),
+    "astc_b200_stream_create": (C.c_int, [C.POINTER(C.c_void_p)]),
+    "astc_b200_stream_destroy": (C.c_int, [C.c_void_p]),
+    "astc_b200_stream_synchronize": (C.c_int, [C.c_void_p]),
+    "astc_b200_save_astc": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
+    "astc_b200_load_astc": (C.c_int, [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                      C.POINTER(C.c_int), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "astc_b200_load_image": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                       C.POINTER(C.c_void_p)]),
+    "astc_b200_image_failure_reason": (C.c_char_p, []),
+    "astc_b200_free_host_buffer": (None, [C.c_void_p]),
+}
+
+
+def lib() -> C.CDLL:
+    """The native library.  Raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not _LIB_PATH.exists():
+            raise ImportError(
+                f"{_LIB_PATH} is missing: build it with `python -m astc_encoder_b200.build` "
+                "(or __graft_entry__.build()); there is no CPU fallback")
+        l = C.CDLL(str(_LIB_PATH))
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def _check(status: int, where: str) -> None:
+    if status != 0:
+        raise AstcError(status, where)
+
+
+def version() -> str:
+    return lib().astc_b200_version().decode()
+
+
+def launch_count() -> int:
+    return int(lib().astc_b200_launch_count())
+
+
+# ---------------------------------------------------------------- geometry --
+def block_dim(option: encode_option) -> int:
+    o = option._abi()
+    return int(lib().astc_b200_block_dim(C.byref(o)))
+
+
+def block_counts(width: int, height: int, option: encode_option) -> tuple[int, int]:
+    o = option._abi()
+    bx, by = C.c_int(), C.c_int()
+    _check(lib().astc_b200_block_counts(width, height, C.byref(o), C.byref(bx), C.byref(by)), "block_counts")
+    return bx.value, by.value
+
+
+def output_size(width: int, height: int, option: encode_option) -> int:
+    o = option._abi()
+    return int(lib().astc_b200_output_size(width, height, C.byref(o)))
+
+
+def band(width: int, height: int, option: encode_option, parts: int, part: int) -> tuple[int, int, int, int]:
+    """(y0, rows, block_byte_offset, block_bytes) of band `part` of `parts`."""
+    o = option._abi()
+    y0, rows, off, nbytes = C.c_int(), C.c_int(), C.c_size_t(), C.c_size_t()
+    _check(lib().astc_b200_band(width, height, C.byref(o), parts, part, C.byref(y0), C.byref(rows),
+                                C.byref(off), C.byref(nbytes)), "band")
+    return y0.value, rows.value, off.value, nbytes.value
+
+
+# ------------------------------------------------------------------ encode --
+def _stream_ptr(stream) -> int:
+    import torch
+    if stream is None:
+        stream = torch.cuda.current_stream()
+    return int(stream.cuda_stream)
+
+
+def _effective(option: encode_option, srgb_texture: Optional[bool]) -> _Option:
+    o = option._abi()
+    if srgb_texture is not None:
+        o.srgb = int(bool(srgb_texture))
+    return o
+
+
+def encode_astc(src, option: encode_option, out=None, stream=None, srgb_texture: Optional[bool] = None):
+    """encode_astc (astc_encode.h:87): `src` is a CUDA uint8 tensor (H, W, 4), rows may be
+    strided; returns a CUDA uint8 tensor (blocks, 16).  Asynchronous on `stream`
+    (default: torch's current stream), like the reference's Dispatch.
+    `srgb_texture` overrides option.srgb the way the texture format does (main.cpp:214)."""
+    import torch
+    if not (isinstance(src, torch.Tensor) and src.is_cuda and src.dtype == torch.uint8 and src.dim() == 3
+            and src.shape[2] == 4 and src.stride(2) == 1 and src.stride(1) == 4):
+        raise ValueError("src must be a CUDA uint8 tensor of shape (H, W, 4) with packed texels")
+    h, w = int(src.shape[0]), int(src.shape[1])
+    pitch = int(src.stride(0)) if h > 1 else w * 4
+    o = _effective(option, srgb_texture)
+    nbytes = int(lib().astc_b200_output_size(w, h, C.byref(o)))
+    if out is None:
+        out = torch.empty((nbytes // BLOCK_BYTES, BLOCK_BYTES), dtype=torch.uint8, device=src.device)
+    elif not (out.is_cuda and out.dtype == torch.uint8 and out.is_contiguous() and out.numel() >= nbytes):
+        raise ValueError("out must be a contiguous CUDA uint8 tensor of at least output_size bytes")
+    with torch.cuda.device(src.device):
+        _check(lib().astc_b200_encode_device(src.data_ptr(), w, h, pitch, C.byref(o), out.data_ptr(),
+                                             _stream_ptr(stream)), "encode_astc")
+    return out
+
+
+def encode_astc_host(rgba: np.ndarray, option: encode_option, out: Optional[np.ndarray] = None,
+                     srgb_texture: Optional[bool] = None) -> np.ndarray:
+    """Upload + encode + read-back in one synchronous call on host memory
+    (load_tex's upload + encode_astc + read_gpu).  rgba: (H, W, 4) uint8."""
+    if rgba.dtype != np.uint8 or rgba.ndim != 3 or rgba.shape[2] != 4 or rgba.strides[2] != 1 or rgba.strides[1] != 4:
+        raise ValueError("rgba must be a uint8 array of shape (H, W, 4) with packed texels")
+    h, w = rgba.shape[:2]
+    o = _effective(option, srgb_texture)
+    nbytes = int(lib().astc_b200_output_size(w, h, C.byref(o)))
+    if out is None:
+        out = np.empty((nbytes // BLOCK_BYTES, BLOCK_BYTES), dtype=np.uint8)
+    pitch = rgba.strides[0] if h > 1 else w * 4
+    _check(lib().astc_b200_encode_host(rgba.ctypes.data, w, h, pitch, C.byref(o), out.ctypes.data), "encode_astc_host")
+    return out
+
+
+def read_gpu(buffer, stream=None) -> np.ndarray:
+    """read_gpu (astc_save.h:34-50): download the block buffer and synchronise."""
+    import torch
+    host = torch.empty(buffer.shape, dtype=buffer.dtype, pin_memory=True)
+    s = _stream_ptr(stream)
+    _check(lib().astc_b200_memcpy_d2h(host.data_ptr(), buffer.data_ptr(), buffer.numel(), s), "read_gpu")
+    _check(lib().astc_b200_stream_synchronize(s), "read_gpu")
+    return host.numpy().copy()
+
+
+class Batch:
+    """Many textures (e.g. all mips of many chains) encoded by ONE kernel launch
+    over a prefix-summed block table (astc_b200_batch_*).  Keeps the tensors alive."""
+
+    def __init__(self, sources: Sequence, option: encode_option, outputs: Optional[Sequence] = None):
+        import torch
+        self.option = option
+        self.sources = list(sources)
+        o = option._abi()
+        if outputs is None:
+            outputs = [torch.empty((output_size(int(s.shape[1]), int(s.shape[0]), option) // BLOCK_BYTES, BLOCK_BYTES),
+                                   dtype=torch.uint8, device=s.device) for s in self.sources]
+        self.outputs = list(outputs)
+        imgs = (_Image * max(1, len(self.sources)))()
+        for i, (s, d) in enumerate(zip(self.sources, self.outputs)):
+            h, w = int(s.shape[0]), int(s.shape[1])
+            imgs[i] = _Image(s.data_ptr(), d.data_ptr(), int(s.stride(0)) if h > 1 else w * 4, w, h)
+        self._handle = C.c_void_p()
+        _check(lib().astc_b200_batch_create(imgs, len(self.sources), C.byref(o), C.byref(self._handle)), "Batch")
+        nb, nt = C.c_uint64(), C.c_uint64()
+        lib().astc_b200_batch_total_blocks(self._handle, C.byref(nb), C.byref(nt))
+        self.total_blocks, self.total_texels = nb.value, nt.value
+
+    def encode(self, stream=None):
+        _check(lib().astc_b200_batch_encode(self._handle, _stream_ptr(stream)), "Batch.encode")
+        return self.outputs
+
+    def close(self):
+        if getattr(self, "_handle", None):
+            lib().astc_b200_batch_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def decode_astc(blocks, width: int, height: int, dim: int, stream=None):
+    """Device decode of the subset this encoder emits -> CUDA uint8 (H, W, 4)."""
+    import torch
+    out = torch.empty((height, width, 4), dtype=torch.uint8, device=blocks.device)
+    _check(lib().astc_b200_decode_device(blocks.data_ptr(), width, height, dim, out.data_ptr(), width * 4,
+                                         _stream_ptr(stream)), "decode_astc")
+    return out
+
+
+def bise_encode(values, quant: int, stream=None):
+    """values: CUDA uint8 (nseq, count).  Returns CUDA uint8 (nseq, 16) ISE streams."""
+    import torch
+    values = values.contiguous()
+    nseq, count = int(values.shape[0]), int(values.shape[1])
+    out = torch.zeros((nseq, 16), dtype=torch.uint8, device=values.device)
+    _check(lib().astc_b200_bise_encode_device(values.data_ptr(), count, quant, nseq, out.data_ptr(),
+                                              _stream_ptr(stream)), "bise_encode")
+    return out
+
+
+def unorm_lut(srgb: bool) -> np.ndarray:
+    out = (C.c_float * 256)()
+    _check(lib().astc_b200_unorm_lut(int(bool(srgb)), out), "unorm_lut")
+    return np.frombuffer(bytes(out), dtype=np.float32).copy()
+
+
+# --------------------------------------------------------------- host files --
+def save_astc(astc_path: str, xdim: int, ydim: int, xsize: int, ysize: int, buffer) -> None:
+    """save_astc (astc_save.h:52-76), byte-exact header + raw blocks."""
+    buf = np.ascontiguousarray(np.asarray(buffer, dtype=np.uint8))
+    _check(lib().astc_b200_save_astc(str(astc_path).encode(), xdim, ydim, xsize, ysize, buf.ctypes.data, buf.size),
+           "save_astc")
+
+
+def load_astc(astc_path: str) -> tuple[int, int, int, int, np.ndarray]:
+    """Returns (xdim, ydim, xsize, ysize, blocks (n, 16) uint8)."""
+    xd, yd, xs, ys = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    p, n = C.c_void_p(), C.c_size_t()
+    _check(lib().astc_b200_load_astc(str(astc_path).encode(), C.byref(xd), C.byref(yd), C.byref(xs), C.byref(ys),
+                                     C.byref(p), C.byref(n)), "load_astc")
+    try:
+        blocks = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n.value,)).copy() if n.value else \
+            np.zeros(0, np.uint8)
+    finally:
+        lib().astc_b200_free_host_buffer(p)
+    return xd.value, yd.value, xs.value, ys.value, blocks.reshape(-1, 16)
+
+
+def load_image(path: str, flip_vertically: bool = True) -> np.ndarray:
+    """stbi_load(path, ..., STBI_rgb_alpha) with the reference's vertical flip
+    (main.cpp:24-25).  Returns (H, W, 4) uint8."""
+    w, h, comp = C.c_int(), C.c_int(), C.c_int()
+    p = C.c_void_p()
+    rc = lib().astc_b200_load_image(str(path).encode(), int(flip_vertically), C.byref(w), C.byref(h), C.byref(comp),
+                                    C.byref(p))
+    if rc != 0:
+        raise AstcError(rc, f"load_image({path}): {lib().astc_b200_image_failure_reason().decode()}")
+    try:
+        arr = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(h.value, w.value, 4)).copy()
+    finally:
+        lib().astc_b200_free_host_buffer(p)
+    return arr
+
+
+def load_tex(tex_path: str, device="cuda", flip_vertically: bool = True):
+    """load_tex (main.cpp:19-56): decode, flip, force RGBA8, upload -> CUDA tensor."""
+    import torch
+    return torch.from_numpy(load_image(tex_path, flip_vertically)).to(device)

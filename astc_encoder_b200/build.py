@@ -1,0 +1,84 @@
+"""In-tree build of the native library (libastc_b200.so) and the astc_cs_enc CLI.
+
+Everything is compiled for sm_100a only; nvcc cross-compiles without a GPU.
+The float flags matter for parity: -fmad=false (no implicit contraction; every
+FMA in the kernels is an explicit intrinsic), IEEE div/sqrt (nvcc defaults,
+never --use_fast_math).
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+CSRC = PKG / "csrc"
+INCLUDE = PKG.parent / "include"
+LIB = PKG / "libastc_b200.so"
+CLI = PKG / "bin" / "astc_cs_enc"
+
+NVCC_FLAGS = [
+    "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+    "--expt-relaxed-constexpr", "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden,-ffp-contract=off", "-I", str(INCLUDE), "-I", str(CSRC),
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: the sm_100a extension cannot be built")
+
+
+def _host_cxx() -> str:
+    # the image exports CXX=/opt/gcc/bin/g++ (a wrapper); the system compiler is the known-good one
+    return "/usr/bin/g++" if os.access("/usr/bin/g++", os.X_OK) else "g++"
+
+
+def _stale(target: Path, sources) -> bool:
+    if not target.exists():
+        return True
+    t = target.stat().st_mtime
+    return any(Path(s).stat().st_mtime > t for s in sources)
+
+
+def _run(cmd, verbose):
+    if verbose:
+        print("+", " ".join(map(str, cmd)), flush=True)
+    res = subprocess.run(list(map(str, cmd)), capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError(f"build step failed: {' '.join(map(str, cmd[:3]))} ...")
+    if verbose and (res.stdout.strip() or res.stderr.strip()):
+        print((res.stdout + res.stderr).strip())
+
+
+def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) -> Path:
+    nvcc = _nvcc()
+    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + \
+        list(CSRC.glob("*.inc")) + list(CSRC.glob("*.cpp")) + list(INCLUDE.glob("*.h")) + [Path(__file__)]
+    objdir = PKG / "_obj"
+    if force or _stale(LIB, deps):
+        objdir.mkdir(exist_ok=True)
+        objs = []
+        for src in ("astc_kernels.cu", "astc_capi.cu", "image_io.cpp"):
+            obj = objdir / (src.rsplit(".", 1)[0] + ".o")
+            if force or _stale(obj, deps):
+                extra = ["-Xptxas", "-v"] if (ptxas_info and src.endswith(".cu")) else []
+                _run([nvcc, "-ccbin", _host_cxx(), *NVCC_FLAGS, *extra, "-c", CSRC / src, "-o", obj],
+                     verbose or ptxas_info)
+            objs.append(obj)
+        _run([nvcc, "-ccbin", _host_cxx(), "-shared", "-o", LIB, *objs, "-lz"], verbose)
+    if force or _stale(CLI, deps + [LIB]):
+        CLI.parent.mkdir(exist_ok=True)
+        _run([_host_cxx(), "-std=c++17", "-O2", "-I", INCLUDE, CSRC / "astc_cs_enc.cpp", "-o", CLI,
+              f"-L{PKG}", "-lastc_b200", "-Wl,-rpath,$ORIGIN/.."], verbose)
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose=True, ptxas_info="--ptxas" in sys.argv)
+    print(LIB)

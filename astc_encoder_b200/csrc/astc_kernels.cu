@@ -1,0 +1,464 @@
+// astc_kernels.cu -- sm_100a kernels: texel fetch + block encode + store,
+// the generic BISE packer (known-answer tests) and the subset decoder.
+//
+// Replaces MainCS (ASTC_Encode.hlsl:553-582) and the Dispatch geometry of
+// astc_encode.h:124-134,190.  Layout in HBM: the source is RGBA8 row-major with
+// an arbitrary pitch; the output is one uint4 per block, row-major blocks.
+#include "astc_kernels.h"
+
+#include <cuda_runtime.h>
+
+#include "astc_block.cuh"
+
+namespace astc {
+
+// ---------------------------------------------------------------------------
+// constant tables
+// ---------------------------------------------------------------------------
+struct TritScatter { uint32_t v[243]; };
+
+template <int METHOD>
+constexpr TritScatter make_trit_scatter()
+{
+    TritScatter s{};
+    const TritPack p = make_trit_pack();
+    for (int i = 0; i < 243; ++i) s.v[i] = dev::WeightPack<METHOD>::scatter(p.v[i]);
+    return s;
+}
+
+__constant__ TritScatter c_trit_scatter_q6 = make_trit_scatter<QUANT_6>();
+__constant__ TritScatter c_trit_scatter_q12 = make_trit_scatter<QUANT_12>();
+__constant__ TritPack c_trit_pack = make_trit_pack();
+__constant__ QuintPack c_quint_pack = make_quint_pack();
+__constant__ WeightTables c_weight_tables = make_weight_tables();
+
+static const float h_srgb_lut[256] = {
+#include "srgb_lut.inc"
+};
+__constant__ float c_srgb_lut[256] = {
+#include "srgb_lut.inc"
+};
+
+const float *host_srgb_lut() { return h_srgb_lut; }
+
+// ---------------------------------------------------------------------------
+// UNORM8 -> float
+// ---------------------------------------------------------------------------
+// c/255.0f correctly rounded for every byte: q = c*r, one Newton correction.
+// (Exhaustively equal to IEEE division for c in 0..255; see selftest() in
+// astc_capi.cu and tests/test_host_math.py.)
+__device__ __forceinline__ float unorm_linear(float c)
+{
+    const float r = 0x1.010102p-8f;                       // RN(1/255)
+    const float q = dev::fmul(c, r);
+    return dev::ffma(dev::ffma(-255.0f, q, c), r, q);
+}
+
+// Byte `sel` of a packed RGBA8 word as an exact float: splice it into the
+// mantissa of 2^23 and subtract 2^23 (two full-rate ALU ops, no I2F).
+template <int SEL>
+__device__ __forceinline__ float byte_to_float(uint32_t w)
+{
+    const uint32_t bits = __byte_perm(w, 0x4B000000u, 0x7440 | SEL);   // {0x4B,0x00,0x00,byte}
+    return dev::fsub(__uint_as_float(bits), 8388608.0f);
+}
+
+template <bool SRGB>
+__device__ __forceinline__ float4 unorm_texel(uint32_t w, const float *lut_rgb)
+{
+    float4 r;
+    if (SRGB) {
+        r.x = lut_rgb[w & 0xFFu];
+        r.y = lut_rgb[(w >> 8) & 0xFFu];
+        r.z = lut_rgb[(w >> 16) & 0xFFu];
+    } else {
+        r.x = unorm_linear(byte_to_float<0>(w));
+        r.y = unorm_linear(byte_to_float<1>(w));
+        r.z = unorm_linear(byte_to_float<2>(w));
+    }
+    r.w = unorm_linear(byte_to_float<3>(w));          // alpha is never sRGB-decoded
+    return r;
+}
+
+// ---------------------------------------------------------------------------
+// block location
+// ---------------------------------------------------------------------------
+struct Located {
+    const uint8_t *rgba;
+    uint4 *out;
+    size_t pitch;
+    int width, height, bx, by;
+    uint32_t flags;
+};
+
+// Single image: divide the linear id.  Batch: binary search the prefix table.
+template <bool BATCH>
+__device__ __forceinline__ bool locate(const EncodeParams &p, uint64_t id, Located &loc)
+{
+    if (id >= p.total_blocks) return false;
+    ImageDesc d = p.single;
+    if (BATCH) {
+        const ImageDesc *__restrict__ table = p.table;
+        int lo = 0, hi = p.count - 1;
+        while (lo < hi) {                                  // last image with first_block <= id
+            const int mid = (lo + hi + 1) >> 1;
+            if (__ldg(&table[mid].first_block) <= id) lo = mid; else hi = mid - 1;
+        }
+        d = table[lo];
+    }
+    const uint32_t local = uint32_t(id - d.first_block);
+    loc.by = int(local / d.blocks_x);
+    loc.bx = int(local - uint32_t(loc.by) * d.blocks_x);
+    loc.rgba = d.rgba;
+    loc.out = reinterpret_cast<uint4 *>(d.blocks) + local;
+    loc.pitch = d.pitch;
+    loc.width = d.width;
+    loc.height = d.height;
+    loc.flags = d.flags;
+    return true;
+}
+
+template <bool ALPHA>
+__device__ __forceinline__ void load_shared_tables(uint32_t *trit_scattered)
+{
+    const TritScatter &src = ALPHA ? c_trit_scatter_q6 : c_trit_scatter_q12;
+    for (int i = threadIdx.x; i < 243; i += blockDim.x) trit_scattered[i] = src.v[i];
+}
+
+// ---------------------------------------------------------------------------
+// 4x4: sixteen texels live in registers as UNORM floats.
+// ---------------------------------------------------------------------------
+struct Texels4x4 {
+    float4 t[16];
+    __device__ __forceinline__ float4 raw(int k) const { return t[k]; }
+    __device__ __forceinline__ void fence() const {}
+};
+
+constexpr int kThreads4x4 = 128;
+
+template <bool ALPHA, bool NORMAL, bool SRGB, bool BATCH>
+__global__ void __launch_bounds__(kThreads4x4)
+encode4x4_kernel(const EncodeParams p)
+{
+    __shared__ uint32_t s_trit[243];
+    __shared__ float s_lut[SRGB ? 256 : 1];
+    load_shared_tables<ALPHA>(s_trit);
+    if (SRGB) for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = c_srgb_lut[i];
+    __syncthreads();
+
+    const uint64_t id = uint64_t(blockIdx.x) * kThreads4x4 + threadIdx.x;
+    Located loc;
+    if (!locate<BATCH>(p, id, loc)) return;
+
+    Texels4x4 tx;
+    const int x0 = loc.bx * 4, y0 = loc.by * 4;
+    const uint8_t *base = loc.rgba + size_t(y0) * loc.pitch + size_t(x0) * 4u;
+    if ((loc.flags & kFlagAligned16) && x0 + 4 <= loc.width && y0 + 4 <= loc.height) {
+        // interior: one 16-byte read-only load per texel row; adjacent threads
+        // read adjacent 16 B, i.e. 512 contiguous bytes per warp per row.
+        uint4 rows[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) rows[r] = __ldg((const uint4 *)(base + size_t(r) * loc.pitch));
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            tx.t[4 * r + 0] = unorm_texel<SRGB>(rows[r].x, s_lut);
+            tx.t[4 * r + 1] = unorm_texel<SRGB>(rows[r].y, s_lut);
+            tx.t[4 * r + 2] = unorm_texel<SRGB>(rows[r].z, s_lut);
+            tx.t[4 * r + 3] = unorm_texel<SRGB>(rows[r].w, s_lut);
+        }
+    } else {
+        // edge / unaligned: per-texel loads, out-of-range texels read as 0
+        // like Texture2D.Load (ASTC_Encode.hlsl:574).
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int x = x0 + (k & 3), y = y0 + (k >> 2);
+            const bool inside = x < loc.width && y < loc.height;
+            const uint32_t w = inside ? __ldg((const uint32_t *)(base + size_t(k >> 2) * loc.pitch + size_t(k & 3) * 4u)) : 0u;
+            tx.t[k] = inside ? unorm_texel<SRGB>(w, s_lut) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    if (NORMAL) {                                         // ASTC_Encode.hlsl:575-578
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { tx.t[k].z = 1.0f; tx.t[k].w = 1.0f; }
+    }
+    *loc.out = dev::encode_block<4, ALPHA>(tx, s_trit);   // one coalesced 16-byte store per thread
+}
+
+// ---------------------------------------------------------------------------
+// 6x6: 36 texels do not fit registers as floats; each thread parks its block
+// as float4[36] in its own shared-memory column (conflict-free: bank = lane).
+// ---------------------------------------------------------------------------
+constexpr int kThreads6x6 = 128;
+
+struct Texels6x6 {
+    const float4 *col;                                    // &smem[threadIdx.x], stride kThreads6x6
+    __device__ __forceinline__ float4 raw(int k) const { return col[k * kThreads6x6]; }
+    __device__ __forceinline__ void fence() const { asm volatile("" ::: "memory"); }
+};
+
+template <bool ALPHA, bool NORMAL, bool SRGB, bool BATCH>
+__global__ void __launch_bounds__(kThreads6x6, 3)
+encode6x6_kernel(const EncodeParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4 *s_tex = reinterpret_cast<float4 *>(smem_raw);                   // [36][kThreads6x6]
+    uint32_t *s_trit = reinterpret_cast<uint32_t *>(s_tex + 36 * kThreads6x6);
+    float *s_lut = reinterpret_cast<float *>(s_trit + 244);
+    load_shared_tables<ALPHA>(s_trit);
+    if (SRGB) for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = c_srgb_lut[i];
+    __syncthreads();
+
+    const uint64_t id = uint64_t(blockIdx.x) * kThreads6x6 + threadIdx.x;
+    Located loc;
+    if (!locate<BATCH>(p, id, loc)) return;
+
+    float4 *col = s_tex + threadIdx.x;
+    const int x0 = loc.bx * 6, y0 = loc.by * 6;
+    const uint8_t *base = loc.rgba + size_t(y0) * loc.pitch + size_t(x0) * 4u;
+    if ((loc.flags & kFlagAligned8) && x0 + 6 <= loc.width && y0 + 6 <= loc.height) {
+        // interior: a block row is 24 B = three 8-byte loads; a warp covers 768
+        // contiguous bytes per texel row.
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            const uint2 *src = (const uint2 *)(base + size_t(r) * loc.pitch);
+            const uint2 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
+            col[(6 * r + 0) * kThreads6x6] = unorm_texel<SRGB>(a.x, s_lut);
+            col[(6 * r + 1) * kThreads6x6] = unorm_texel<SRGB>(a.y, s_lut);
+            col[(6 * r + 2) * kThreads6x6] = unorm_texel<SRGB>(b.x, s_lut);
+            col[(6 * r + 3) * kThreads6x6] = unorm_texel<SRGB>(b.y, s_lut);
+            col[(6 * r + 4) * kThreads6x6] = unorm_texel<SRGB>(c.x, s_lut);
+            col[(6 * r + 5) * kThreads6x6] = unorm_texel<SRGB>(c.y, s_lut);
+        }
+    } else {
+#pragma unroll 6
+        for (int k = 0; k < 36; ++k) {
+            const int kx = k % 6, ky = k / 6;
+            const bool inside = x0 + kx < loc.width && y0 + ky < loc.height;
+            const uint32_t w = inside ? __ldg((const uint32_t *)(base + size_t(ky) * loc.pitch + size_t(kx) * 4u)) : 0u;
+            col[k * kThreads6x6] = inside ? unorm_texel<SRGB>(w, s_lut) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    if (NORMAL) {
+#pragma unroll 6
+        for (int k = 0; k < 36; ++k) {
+            float4 v = col[k * kThreads6x6];
+            v.z = 1.0f; v.w = 1.0f;
+            col[k * kThreads6x6] = v;
+        }
+    }
+    // each thread reads back only its own column: no barrier needed
+    Texels6x6 tx{col};
+    *loc.out = dev::encode_block<6, ALPHA>(tx, s_trit);
+}
+
+constexpr size_t kSmem6x6 = size_t(36) * kThreads6x6 * sizeof(float4) + 244 * sizeof(uint32_t) + 256 * sizeof(float);
+
+// ---------------------------------------------------------------------------
+// launch
+// ---------------------------------------------------------------------------
+template <bool ALPHA, bool NORMAL, bool SRGB, bool BATCH>
+static cudaError_t launch_variant(int dim, const EncodeParams &p, cudaStream_t stream)
+{
+    if (dim == 4) {
+        const uint64_t ctas = (p.total_blocks + kThreads4x4 - 1) / kThreads4x4;
+        if (ctas > 0x7FFFFFFFull) return cudaErrorInvalidConfiguration;
+        encode4x4_kernel<ALPHA, NORMAL, SRGB, BATCH><<<unsigned(ctas), kThreads4x4, 0, stream>>>(p);
+    } else {
+        const uint64_t ctas = (p.total_blocks + kThreads6x6 - 1) / kThreads6x6;
+        if (ctas > 0x7FFFFFFFull) return cudaErrorInvalidConfiguration;
+        auto kern = encode6x6_kernel<ALPHA, NORMAL, SRGB, BATCH>;
+        static thread_local int configured_device = -1;
+        int devno = 0;
+        cudaGetDevice(&devno);
+        if (configured_device != devno) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmem6x6));
+            if (e != cudaSuccess) return e;
+            configured_device = devno;
+        }
+        kern<<<unsigned(ctas), kThreads6x6, kSmem6x6, stream>>>(p);
+    }
+    return cudaGetLastError();
+}
+
+template <bool BATCH>
+static cudaError_t dispatch(int dim, bool alpha, bool normal, bool srgb, const EncodeParams &p, cudaStream_t s)
+{
+    // IS_NORMALMAP / HAS_ALPHA macros of astc_encode.h:55-62 become template
+    // parameters; sRGB is dropped for normal maps (main.cpp:214).
+    if (normal) srgb = false;
+    const int key = (alpha ? 4 : 0) | (normal ? 2 : 0) | (srgb ? 1 : 0);
+    switch (key) {
+    case 0: return launch_variant<false, false, false, BATCH>(dim, p, s);
+    case 1: return launch_variant<false, false, true, BATCH>(dim, p, s);
+    case 2: return launch_variant<false, true, false, BATCH>(dim, p, s);
+    case 4: return launch_variant<true, false, false, BATCH>(dim, p, s);
+    case 5: return launch_variant<true, false, true, BATCH>(dim, p, s);
+    case 6: return launch_variant<true, true, false, BATCH>(dim, p, s);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_encode(int dim, bool alpha, bool normal, bool srgb, const EncodeParams &p, cudaStream_t stream)
+{
+    if (p.total_blocks == 0) return cudaSuccess;
+    return p.count > 1 || p.table != nullptr ? dispatch<true>(dim, alpha, normal, srgb, p, stream)
+                                             : dispatch<false>(dim, alpha, normal, srgb, p, stream);
+}
+
+// ---------------------------------------------------------------------------
+// Generic BISE packer: bits, trits and quints for every QUANT_* level
+// (ASTC_IntegerSequenceEncoding.hlsl:142-276).  One thread per sequence.
+// ---------------------------------------------------------------------------
+struct BitStream128 {
+    uint64_t lo = 0, hi = 0;
+    uint32_t pos = 0;
+    // orbits8_ptr (:98-119) without its shift-by-32 hazard
+    __device__ __forceinline__ void put(uint32_t value, uint32_t count)
+    {
+        if (count == 0 || pos >= 128) { pos += count; return; }
+        const uint64_t v = uint64_t(value) & ((1ull << count) - 1ull);
+        if (pos < 64) {
+            lo |= v << pos;
+            if (pos + count > 64) hi |= v >> (64 - pos);
+        } else {
+            hi |= v << (pos - 64);
+        }
+        pos += count;
+    }
+};
+
+__global__ void bise_encode_kernel(const uint8_t *__restrict__ values, int count, int quant, int nseq,
+                                   uint4 *__restrict__ streams)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nseq) return;
+    const uint8_t *v = values + size_t(s) * size_t(count);
+    const QuantLayout l = quant_layout(quant);
+    const uint32_t mask = (1u << l.bits) - 1u;
+    BitStream128 bs;
+    if (l.trits) {
+        for (int i = 0; i < count; i += 5) {
+            uint32_t g[5];
+            for (int j = 0; j < 5; ++j) g[j] = i + j < count ? v[i + j] : 0u;
+            const uint32_t T = c_trit_pack.v[(g[4] >> l.bits) * 81 + (g[3] >> l.bits) * 27 + (g[2] >> l.bits) * 9 +
+                                             (g[1] >> l.bits) * 3 + (g[0] >> l.bits)];
+            bs.put(g[0] & mask, l.bits); bs.put(T & 3u, 2);
+            bs.put(g[1] & mask, l.bits); bs.put((T >> 2) & 3u, 2);
+            bs.put(g[2] & mask, l.bits); bs.put((T >> 4) & 1u, 1);
+            bs.put(g[3] & mask, l.bits); bs.put((T >> 5) & 3u, 2);
+            bs.put(g[4] & mask, l.bits); bs.put((T >> 7) & 1u, 1);
+        }
+    } else if (l.quints) {
+        for (int i = 0; i < count; i += 3) {
+            uint32_t g[3];
+            for (int j = 0; j < 3; ++j) g[j] = i + j < count ? v[i + j] : 0u;
+            const uint32_t Q = c_quint_pack.v[(g[2] >> l.bits) * 25 + (g[1] >> l.bits) * 5 + (g[0] >> l.bits)];
+            bs.put(g[0] & mask, l.bits); bs.put(Q & 7u, 3);
+            bs.put(g[1] & mask, l.bits); bs.put((Q >> 3) & 3u, 2);
+            bs.put(g[2] & mask, l.bits); bs.put((Q >> 5) & 3u, 2);
+        }
+    } else {
+        for (int i = 0; i < count; ++i) bs.put(v[i], l.bits);
+    }
+    streams[s] = make_uint4(uint32_t(bs.lo), uint32_t(bs.lo >> 32), uint32_t(bs.hi), uint32_t(bs.hi >> 32));
+}
+
+cudaError_t launch_bise(const uint8_t *d_values, int count, int quant, int nseq, uint8_t *d_streams, cudaStream_t stream)
+{
+    if (nseq == 0) return cudaSuccess;
+    bise_encode_kernel<<<(nseq + 127) / 128, 128, 0, stream>>>(d_values, count, quant, nseq, (uint4 *)d_streams);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// Subset decoder (ASTC spec C.2; the reference has none).  One thread per
+// block; handles what this encoder emits: 1 partition, 1 plane, CEM 8 / 12,
+// 8-bit endpoints, 4x4 weight grid with QUANT_6 / QUANT_12 weights.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t bits128(const uint4 b, uint32_t pos, uint32_t count)
+{
+    const uint32_t w[5] = {b.x, b.y, b.z, b.w, 0u};
+    const uint32_t i = pos >> 5, s = pos & 31u;
+    const uint64_t two = (uint64_t(w[i + 1 > 4 ? 4 : i + 1]) << 32) | w[i];
+    return uint32_t(two >> s) & ((1u << count) - 1u);
+}
+
+__global__ void decode_kernel(const uint4 *__restrict__ blocks, int width, int height, int dim,
+                              uint8_t *__restrict__ rgba, size_t pitch, uint32_t total, uint32_t bw)
+{
+    const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= total) return;
+    const uint4 b = __ldg(blocks + id);
+    const uint32_t mode = b.x & 0x7FFu, cem = (b.x >> 13) & 0xFu, parts = (b.x >> 11) & 3u;
+    const uint32_t by = id / bw, bx = id - by * bw;
+    const bool rgba_mode = mode == blockmode_4x4grid(QUANT_6) && cem == CEM_LDR_RGBA_DIRECT;
+    const bool rgb_mode = mode == blockmode_4x4grid(QUANT_12) && cem == CEM_LDR_RGB_DIRECT;
+    int wq[16];
+    int e0[4], e1[4];
+    if ((rgba_mode || rgb_mode) && parts == 0) {
+        const int method = rgba_mode ? QUANT_6 : QUANT_12;
+        const uint32_t n = rgba_mode ? 1u : 2u, gbits = 5u * n + 8u;
+        // weight stream = block bits read downward from bit 127
+        const uint4 rev = make_uint4(__brev(b.w), __brev(b.z), __brev(b.y), __brev(b.x));
+        for (int g = 0; g < 4; ++g) {
+            const uint32_t grp = bits128(rev, g * gbits, gbits);
+            const uint32_t T = ((grp >> n) & 3u) | (((grp >> (2 * n + 2)) & 3u) << 2) | (((grp >> (3 * n + 4)) & 1u) << 4) |
+                               (((grp >> (4 * n + 5)) & 3u) << 5) | (((grp >> (5 * n + 7)) & 1u) << 7);
+            const Trits t = trits_from_integer(int(T));
+            const uint32_t m[5] = {grp & ((1u << n) - 1u), (grp >> (n + 2)) & ((1u << n) - 1u), (grp >> (2 * n + 4)) & ((1u << n) - 1u),
+                                   (grp >> (3 * n + 5)) & ((1u << n) - 1u), (grp >> (4 * n + 7)) & ((1u << n) - 1u)};
+            for (int j = 0; j < 5 && 5 * g + j < 16; ++j)
+                wq[5 * g + j] = c_weight_tables.unq[method][((uint32_t(t.t[j]) << n) | m[j]) & 31u];
+        }
+        int ep[8];
+        for (int i = 0; i < 8; ++i) ep[i] = int(bits128(b, 17u + 8u * i, 8));
+        if (rgb_mode) { ep[6] = 255; ep[7] = 255; }
+        if (ep[1] + ep[3] + ep[5] >= ep[0] + ep[2] + ep[4]) {
+            for (int c = 0; c < 4; ++c) { e0[c] = ep[2 * c]; e1[c] = ep[2 * c + 1]; }
+        } else {                                           // blue contraction (spec C.2.14)
+            e0[0] = (ep[1] + ep[5]) >> 1; e0[1] = (ep[3] + ep[5]) >> 1; e0[2] = ep[5]; e0[3] = ep[7];
+            e1[0] = (ep[0] + ep[4]) >> 1; e1[1] = (ep[2] + ep[4]) >> 1; e1[2] = ep[4]; e1[3] = ep[6];
+        }
+    } else {
+        for (int i = 0; i < 16; ++i) wq[i] = 0;
+        e0[0] = e1[0] = 255; e0[1] = e1[1] = 0; e0[2] = e1[2] = 255; e0[3] = e1[3] = 255;   // error colour
+    }
+    const int Ds = (1024 + dim / 2) / (dim - 1);
+    for (int y = 0; y < dim; ++y) {
+        const int py = int(by) * dim + y;
+        if (py >= height) break;
+        for (int x = 0; x < dim; ++x) {
+            const int px = int(bx) * dim + x;
+            if (px >= width) break;
+            // infill of the 4x4 grid (spec C.2.18)
+            const int gs = (Ds * x * 3 + 32) >> 6, gt = (Ds * y * 3 + 32) >> 6;
+            const int js = gs >> 4, fs = gs & 15, jt = gt >> 4, ft = gt & 15;
+            const int v0 = js + jt * 4;
+            const int w11 = (fs * ft + 8) >> 4, w10 = ft - w11, w01 = fs - w11, w00 = 16 - fs - ft + w11;
+            const int p00 = wq[v0], p01 = v0 + 1 < 16 ? wq[v0 + 1] : 0;
+            const int p10 = v0 + 4 < 16 ? wq[v0 + 4] : 0, p11 = v0 + 5 < 16 ? wq[v0 + 5] : 0;
+            const int w = (p00 * w00 + p01 * w01 + p10 * w10 + p11 * w11 + 8) >> 4;
+            uint32_t px4 = 0;
+            for (int c = 0; c < 4; ++c) {
+                const int c0 = (e0[c] << 8) | e0[c], c1 = (e1[c] << 8) | e1[c];
+                const int v = (c0 * (64 - w) + c1 * w + 32) >> 6;
+                px4 |= uint32_t(v >> 8) << (8 * c);
+            }
+            *(uint32_t *)(rgba + size_t(py) * pitch + size_t(px) * 4u) = px4;
+        }
+    }
+}
+
+cudaError_t launch_decode(const uint8_t *d_blocks, int width, int height, int dim, uint8_t *d_rgba, size_t pitch,
+                          cudaStream_t stream)
+{
+    const uint32_t bw = uint32_t((width + dim - 1) / dim), bh = uint32_t((height + dim - 1) / dim);
+    const uint64_t total = uint64_t(bw) * bh;
+    if (total == 0) return cudaSuccess;
+    if (total > 0xFFFFFFFFull) return cudaErrorInvalidConfiguration;
+    decode_kernel<<<unsigned((total + 127) / 128), 128, 0, stream>>>((const uint4 *)d_blocks, width, height, dim, d_rgba,
+                                                                      pitch, uint32_t(total), bw);
+    return cudaGetLastError();
+}
+
+}  // namespace astc

@@ -1,0 +1,40 @@
+// astc_kernels.h -- internal interface between the C ABI (astc_capi.cu) and
+// the sm_100a kernels (astc_kernels.cu).  Not installed.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+
+namespace astc {
+
+enum : uint32_t {
+    kFlagAligned16 = 1u,   // base and pitch are multiples of 16 B (4x4 vector path)
+    kFlagAligned8 = 2u,    // base and pitch are multiples of 8 B  (6x6 vector path)
+};
+
+// One source texture and its output; what the reference passes through the
+// SRV, UAV and constant buffer (astc_encode.h:107-187).
+struct ImageDesc {
+    const uint8_t *rgba;
+    uint8_t *blocks;
+    size_t pitch;
+    uint64_t first_block;    // prefix sum over the batch
+    int32_t width, height;
+    uint32_t blocks_x;       // xBlockNum (astc_encode.h:127)
+    uint32_t flags;
+};
+
+struct EncodeParams {
+    ImageDesc single;            // used when table == nullptr
+    const ImageDesc *table;      // device array, sorted by first_block
+    int32_t count;
+    uint64_t total_blocks;
+};
+
+cudaError_t launch_encode(int dim, bool alpha, bool normal, bool srgb, const EncodeParams &p, cudaStream_t stream);
+cudaError_t launch_bise(const uint8_t *d_values, int count, int quant, int nseq, uint8_t *d_streams, cudaStream_t stream);
+cudaError_t launch_decode(const uint8_t *d_blocks, int width, int height, int dim, uint8_t *d_rgba, size_t pitch,
+                          cudaStream_t stream);
+const float *host_srgb_lut();
+
+}  // namespace astc

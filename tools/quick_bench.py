@@ -1,0 +1,32 @@
+"""Ad-hoc kernel timing used during development (not the contract bench)."""
+import sys, time
+import torch
+sys.path.insert(0, ".")
+import astc_encoder_b200 as A
+from astc_encoder_b200 import synth
+
+def run(w, h, opt, label, iters=10):
+    img = synth.synth_rgba(w, h, 1234, device="cuda")
+    out = A.encode_astc(img, opt)
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
+    for _ in range(3):
+        A.encode_astc(img, opt, out=out)
+    ev[0].record()
+    for i in range(iters):
+        A.encode_astc(img, opt, out=out)
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    ts = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(iters))
+    med = ts[len(ts) // 2]
+    print(f"{label}: {w}x{h} median {med:.3f} ms best {ts[0]:.3f} ms -> {w*h/med/1e6:.1f} Gtexel/s", flush=True)
+
+if __name__ == "__main__":
+    print(A.version(), torch.cuda.get_device_name(0))
+    run(4096, 4096, A.encode_option(), "4x4 rgb")
+    run(4096, 4096, A.encode_option(has_alpha=True), "4x4 rgba")
+    run(4096, 4096, A.encode_option(srgb=True), "4x4 rgb srgb")
+    run(4096, 4096, A.encode_option(is_normal_map=True), "4x4 norm")
+    run(16384, 16384, A.encode_option(), "4x4 rgb")
+    run(8192, 8192, A.encode_option(is6x6=True, has_alpha=True, srgb=True), "6x6 rgba srgb")
+    run(8192, 8192, A.encode_option(is6x6=True), "6x6 rgb")
