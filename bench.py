@@ -1,0 +1,385 @@
+#!/usr/bin/env python3
+"""bench.py -- ASTC encode throughput on B200 (the BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path (texel fetch -> PCA endpoint fit -> weight
+quantisation -> BISE packing -> 128-bit block store) over one synthetic
+16384x16384 RGBA8 texture per GPU, ASTC 4x4, RGB, linear -- the configuration
+north_star quotes its target on.  Multi-GPU shards by texture (one texture of
+the batch per rank, no collective), so scaling is "weak".
+
+value      device-resident throughput, CUDA events on the launching stream,
+           max over ranks (Mtexels/s, all ranks' texels / slowest rank's time).
+e2e        the same metric through the C-ABI host call astc_b200_encode_host():
+           pinned host input -> H2D -> kernel -> D2H -> pinned host output,
+           every step, inside the timed region.
+roofline   HBM roofline of the encode kernel from ALGORITHMIC bytes (5 B/texel
+           at 4x4) over its average launch duration.
+cpu_baseline  the CPU oracle (oracle/, a scalar port of the reference shader)
+           with OpenMP on this host, on a bounded sample of the same texture.
+
+--impl reference: the reference's own implementation cannot run on Linux (HLSL
+cs_5_0 through D3D11), so this arm times the oracle port on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+METRIC = "Mtexels/s ASTC 4x4 encode, 16384x16384 RGBA8 (RGB linear)"
+UNIT = "Mtexels/s"
+W16K = 16384
+BYTES_PER_TEXEL_4x4 = 5.0                  # 4 B read + 16/16 B written
+HBM_FALLBACK_GBS = 6650.0                  # B200_PROFILING.md fallback
+
+
+def _peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            d = json.loads(p.read_text())
+            if "hbm_gbs" in d:
+                return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def _traffic(name: str):
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture."""
+    p = ROOT / "profiles" / "roofline_traffic.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text()).get(name)
+        except Exception:
+            return None
+    return None
+
+
+# --------------------------------------------------------------------- clocks --
+class ClockSampler:
+    """Polls NVML for SM clock and throttle reasons while a timed region runs."""
+    _REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
+                0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting",
+                0x10: "sync_boost"}
+
+    def __init__(self, torch_device_index: int, period_s: float = 0.004):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        self._h = None
+        self.period = period_s
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(torch_device_index).uuid)
+            if not uuid.startswith("GPU-"):
+                uuid = "GPU-" + uuid
+            try:
+                self._h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                self._h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+            self._nv = pynvml
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:                       # noqa: BLE001
+            self._err = repr(e)
+            self._h = None
+
+    def _run(self):
+        nv = self._nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+                for bit, name in self._REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def __enter__(self):
+        if self._h is not None:
+            self._stop.clear()
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join()
+            self._thread = None
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unsampled"]}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------ reference --
+def run_reference(args) -> int:
+    """The reference's CPU-side stand-in: the oracle port on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import numpy as np
+    from astc_encoder_b200 import synth
+    from oracle import oracle as O
+    O.lib()
+    rows_texels = 1024                                           # 16384 x 1024 texels per step
+    img = synth.synth_rgba(W16K, rows_texels, synth.SEED_CFG5).numpy()
+    threads = os.cpu_count() or 1
+    for _ in range(max(1, args.warmup)):
+        _, used = O.encode_rows(img, 0, rows_texels // 4, block_dim=4, threads=0)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _, used = O.encode_rows(img, 0, rows_texels // 4, block_dim=4, threads=0)
+    dt = (time.perf_counter() - t0) / args.steps
+    value = W16K * rows_texels / dt / 1e6
+    sample = f"block rows 0..{rows_texels // 4 - 1} ({W16K}x{rows_texels} texels) of the 16384x16384 texture per step"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "16384x16384 RGBA8, ASTC 4x4, RGB linear", "sample": sample,
+                   "note": "reference hot path is HLSL/D3D11 (not runnable on Linux): timed the scalar C port "
+                           "oracle/astc_oracle.c, OpenMP over block rows"},
+        "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": int(used), "kind": "port", "sample": sample},
+        "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "host_cpus": threads,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------ b200 arm --
+def _time_launches(torch, fn, steps, warmup, flush=None):
+    """Average device time of fn() per call, each call bracketed by events (optionally an L2 flush before)."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    total = 0.0
+    for _ in range(steps):
+        if flush is not None:
+            flush()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        b.synchronize()
+        total += a.elapsed_time(b)
+    return total / steps
+
+
+def run_b200(args) -> int:
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import astc_encoder_b200 as A
+    from astc_encoder_b200 import synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            # convenience: re-launch under torchrun on this node
+            port = os.environ.get("MASTER_PORT", "29531")
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                   "--master-addr", "127.0.0.1", "--master-port", port, str(Path(__file__).resolve()), *sys.argv[1:]]
+            os.execv(sys.executable, cmd)
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the encoder has no CPU path (use --impl reference for the CPU oracle)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    A.lib()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    opt = A.encode_option()                                      # 4x4, RGB, linear
+    tex = synth.synth_rgba(W16K, W16K, synth.SEED_CFG5 + rank, device=dev)   # texture `rank` of the batch
+    out = torch.empty((A.output_size(W16K, W16K, opt) // 16, 16), dtype=torch.uint8, device=dev)
+    texels = W16K * W16K
+    stream = torch.cuda.current_stream()
+    sampler = ClockSampler(local)
+
+    # ---- device-resident: W warm-up, then exactly K timed steps ----
+    for _ in range(args.warmup):
+        A.encode_astc(tex, opt, out=out, stream=stream)
+    launches0 = A.launch_count()
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    with sampler:
+        ev[0].record(stream)
+        for i in range(args.steps):
+            A.encode_astc(tex, opt, out=out, stream=stream)
+            ev[i + 1].record(stream)
+        torch.cuda.synchronize()
+    barrier()
+    launches = A.launch_count() - launches0
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps))
+    ms_per_step = max_over_ranks(total_ms / args.steps)
+    kernel_ms = sum(per) / len(per)                              # == total/steps: launches are back to back
+    value = world * texels / (ms_per_step * 1e-3) / 1e6
+
+    # ---- end to end through the C-ABI host entry point, pinned host buffers ----
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    h_in = torch.empty((W16K, W16K, 4), dtype=torch.uint8, pin_memory=True)
+    h_out = torch.empty((out.shape[0], 16), dtype=torch.uint8, pin_memory=True)
+    h_in.copy_(tex)
+    torch.cuda.synchronize()
+    h_in_np, h_out_np = h_in.numpy(), h_out.numpy()
+    A.encode_astc_host(h_in_np, opt, out=h_out_np)              # warm-up (allocations land in the pool)
+    l0 = A.launch_count()
+    barrier()
+    with sampler:
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            A.encode_astc_host(h_in_np, opt, out=h_out_np)      # synchronous: returns after the D2H copy
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+    barrier()
+    e2e_launches = A.launch_count() - l0
+    e2e_s = max_over_ranks(e2e_s)
+    e2e_value = world * texels / e2e_s / 1e6
+    e2e_identical = bool(torch.equal(h_out, out.cpu()))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = _peaks()
+    achieved = texels * BYTES_PER_TEXEL_4x4 / (kernel_ms * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "16384x16384 RGBA8, ASTC 4x4, RGB linear (one texture per GPU, sharded by texture)",
+                   "blocks_per_gpu": texels // 16, "l2": "input 1 GiB + output 256 MiB per step exceed the 126 MB L2; no flush needed",
+                   "timing": "CUDA events on the launching stream, max over ranks"},
+        "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": texels * 4,
+                "d2h_bytes_per_step": texels, "steps": e2e_steps, "ms_per_step": round(e2e_s * 1e3, 3),
+                "api": "astc_b200_encode_host (C ABI), pinned host buffers", "launches": int(e2e_launches),
+                "matches_device_path": e2e_identical},
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary(),
+        "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                     "frac": round(achieved / peak, 4), "traffic": _traffic("encode4x4_rgb"),
+                     "kernel": "encode4x4_kernel<rgb,linear>", "kernel_ms": round(kernel_ms, 4),
+                     "kernel_ms_best": round(per[0], 4), "algorithmic_bytes_per_launch": int(texels * BYTES_PER_TEXEL_4x4),
+                     "peak_source": peak_src,
+                     "note": "ALU-issue-bound kernel (~1.4k lane-ops per 80 B block): see DESIGN.md for the FP32 roofline"},
+    }
+
+    # ---- CPU baseline + parity on a bounded sample of the same texture (rank 0, N=1) ----
+    if world == 1 and not args.no_cpu:
+        from oracle import oracle as O
+        O.lib()
+        rows_texels = 4096
+        sample = tex[:rows_texels].cpu().numpy()
+        t0 = time.perf_counter()
+        want, used = O.encode_rows(sample, 0, rows_texels // 4, block_dim=4, threads=0)
+        dt = time.perf_counter() - t0
+        got = out[: want.shape[0]].cpu().numpy()
+        same = int((got == want).all(axis=1).sum())
+        line["cpu_baseline"] = {"value": round(W16K * rows_texels / dt / 1e6, 2), "unit": UNIT, "cores": int(used),
+                                "kind": "port", "sample": f"block rows 0..{rows_texels // 4 - 1} ({W16K}x{rows_texels} texels) "
+                                "of the same texture, oracle/astc_oracle.c with OpenMP"}
+        line["parity"] = {"blocks_checked": int(want.shape[0]), "bit_identical": same}
+
+    # ---- the other BASELINE.json configs, kernel-only, L2 flushed between launches ----
+    if world == 1 and not args.no_others:
+        line["others"] = other_configs(torch, A, synth, dev, peak)
+
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def other_configs(torch, A, synth, dev, peak):
+    res = []
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def flush():
+        flush_buf.zero_()
+
+    def one(name, img, opt, dim):
+        out = A.encode_astc(img, opt)
+        ms = _time_launches(torch, lambda: A.encode_astc(img, opt, out=out), 10, 3, flush)
+        h, w = int(img.shape[0]), int(img.shape[1])
+        nbytes = w * h * 4 + out.numel()
+        res.append({"workload": name, "value": round(w * h / ms / 1e3, 1), "unit": UNIT, "kernel_ms": round(ms, 4),
+                    "hbm_frac": round(nbytes / (ms * 1e-3) / 1e9 / peak, 4)})
+
+    one("4096x4096 RGBA8, 4x4, RGB linear", synth.synth_rgba(4096, 4096, synth.SEED_CFG2, device=dev),
+        A.encode_option(), 4)
+    one("8192x8192 RGBA8, 6x6, -alpha -srgb", synth.synth_rgba(8192, 8192, synth.SEED_CFG3, device=dev),
+        A.encode_option(is6x6=True, has_alpha=True, srgb=True), 6)
+    one("4096x4096 normal map, -norm -4x4", synth.synth_normal(4096, 4096, synth.SEED_CFG4, device=dev),
+        A.encode_option(is_normal_map=True), 4)
+    # batch of 2048x2048 mip chains in one launch over a prefix-summed block table
+    chains = 64
+    srcs = []
+    for i in range(chains):
+        srcs.extend(synth.mip_chain(synth.synth_rgba(2048, 2048, synth.SEED_BATCH + i, device=dev)))
+    batch = A.Batch(srcs, A.encode_option())
+    ms = _time_launches(torch, lambda: batch.encode(), 10, 3, None)
+    res.append({"workload": f"{chains} x 2048x2048 12-level mip chains, 4x4 RGB, ONE launch", "value": round(batch.total_texels / ms / 1e3, 1),
+                "unit": UNIT, "kernel_ms": round(ms, 4), "textures": len(srcs), "blocks": int(batch.total_blocks)})
+    batch.close()
+    return res
+
+
+def main() -> int:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU oracle baseline / parity sample")
+    ap.add_argument("--no-others", action="store_true", help="skip the secondary configs")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3                                          # timing rule: W >= 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
