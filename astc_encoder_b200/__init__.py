@@ -30,7 +30,9 @@ __all__ = [
 ]
 
 _PKG = Path(__file__).resolve().parent
-_LIB_PATH = _PKG / "libastc_b200.so"
+import os as _os
+# ASTC_B200_LIB selects an experiment build (tools/variants.py); the product is libastc_b200.so
+_LIB_PATH = Path(_os.environ["ASTC_B200_LIB"]) if _os.environ.get("ASTC_B200_LIB") else _PKG / "libastc_b200.so"
 
 BLOCK_BYTES = 16
 

@@ -56,6 +56,25 @@ def _run(cmd, verbose):
         print((res.stdout + res.stderr).strip())
 
 
+def build_variant(tag: str, defines, verbose: bool = False) -> Path:
+    """Experiment builds (tools/variants.py): libastc_b200_<tag>.so with extra -D flags.
+    Only the kernel TU differs; never used by the product path."""
+    nvcc = _nvcc()
+    objdir = PKG / "_obj"
+    objdir.mkdir(exist_ok=True)
+    lib = PKG / f"libastc_b200_{tag}.so"
+    kobj = objdir / f"astc_kernels_{tag}.o"
+    _run([nvcc, "-ccbin", _host_cxx(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", CSRC / "astc_kernels.cu", "-o", kobj], verbose)
+    objs = [kobj]
+    for src in ("astc_capi.cu", "image_io.cpp"):
+        obj = objdir / (src.rsplit(".", 1)[0] + ".o")
+        if not obj.exists():
+            _run([nvcc, "-ccbin", _host_cxx(), *NVCC_FLAGS, "-c", CSRC / src, "-o", obj], verbose)
+        objs.append(obj)
+    _run([nvcc, "-ccbin", _host_cxx(), "-shared", "-o", lib, *objs, "-lz"], verbose)
+    return lib
+
+
 def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) -> Path:
     nvcc = _nvcc()
     deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + \

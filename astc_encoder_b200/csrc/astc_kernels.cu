@@ -15,19 +15,8 @@ namespace astc {
 // ---------------------------------------------------------------------------
 // constant tables
 // ---------------------------------------------------------------------------
-struct TritScatter { uint32_t v[243]; };
-
-template <int METHOD>
-constexpr TritScatter make_trit_scatter()
-{
-    TritScatter s{};
-    const TritPack p = make_trit_pack();
-    for (int i = 0; i < 243; ++i) s.v[i] = dev::WeightPack<METHOD>::scatter(p.v[i]);
-    return s;
-}
-
-__constant__ TritScatter c_trit_scatter_q6 = make_trit_scatter<QUANT_6>();
-__constant__ TritScatter c_trit_scatter_q12 = make_trit_scatter<QUANT_12>();
+__constant__ dev::TableImage c_tables_q6 = dev::make_table_image<QUANT_6>();
+__constant__ dev::TableImage c_tables_q12 = dev::make_table_image<QUANT_12>();
 __constant__ TritPack c_trit_pack = make_trit_pack();
 __constant__ QuintPack c_quint_pack = make_quint_pack();
 __constant__ WeightTables c_weight_tables = make_weight_tables();
@@ -41,43 +30,73 @@ __constant__ float c_srgb_lut[256] = {
 
 const float *host_srgb_lut() { return h_srgb_lut; }
 
+using dev::f2;
+using dev::Texel;
+
 // ---------------------------------------------------------------------------
 // UNORM8 -> float
 // ---------------------------------------------------------------------------
-// c/255.0f correctly rounded for every byte: q = c*r, one Newton correction.
-// (Exhaustively equal to IEEE division for c in 0..255; see selftest() in
-// astc_capi.cu and tests/test_host_math.py.)
-__device__ __forceinline__ float unorm_linear(float c)
+// c/255.0f correctly rounded for every byte c, as one FMUL + one FFMA (packed: two
+// channels per instruction): 1/255 = kRcpHi + kRcpLo to ~2^-48; kRcpLo has 16
+// significant bits so c*kRcpLo is exact, and the FMA rounds c*(kRcpHi+kRcpLo)
+// once.  Exhaustively equal to IEEE division (tests/test_host_math.py).
+constexpr float kRcpHi = 0x1.010102p-8f;                  // RN(1/255)
+constexpr float kRcpLo = -0x1.fdfep-33f;
+
+__device__ __forceinline__ f2 unorm2(f2 c)
 {
-    const float r = 0x1.010102p-8f;                       // RN(1/255)
-    const float q = dev::fmul(c, r);
-    return dev::ffma(dev::ffma(-255.0f, q, c), r, q);
+    return dev::fma2(c, dev::bc(kRcpHi), dev::mul2(c, dev::bc(kRcpLo)));
+}
+__device__ __forceinline__ float unorm1(float c)
+{
+    return dev::ffma(c, kRcpHi, dev::fmul(c, kRcpLo));
 }
 
-// Byte `sel` of a packed RGBA8 word as an exact float: splice it into the
-// mantissa of 2^23 and subtract 2^23 (two full-rate ALU ops, no I2F).
+// Bytes of a packed RGBA8 word as exact floats: splice each into the mantissa of
+// 2^23 (one PRMT) and subtract 2^23 (packed FADD2) -- no I2F.
 template <int SEL>
-__device__ __forceinline__ float byte_to_float(uint32_t w)
+__device__ __forceinline__ float byte_bits(uint32_t w)
 {
-    const uint32_t bits = __byte_perm(w, 0x4B000000u, 0x7440 | SEL);   // {0x4B,0x00,0x00,byte}
-    return dev::fsub(__uint_as_float(bits), 8388608.0f);
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440 | SEL));   // {0x4B,0x00,0x00,byte}
+}
+__device__ __forceinline__ f2 bytes_lo(uint32_t w)
+{
+    return dev::add2(dev::mk(byte_bits<0>(w), byte_bits<1>(w)), dev::bc(-8388608.0f));
+}
+__device__ __forceinline__ f2 bytes_hi(uint32_t w)
+{
+    return dev::add2(dev::mk(byte_bits<2>(w), byte_bits<3>(w)), dev::bc(-8388608.0f));
 }
 
-template <bool SRGB>
-__device__ __forceinline__ float4 unorm_texel(uint32_t w, const float *lut_rgb)
+// One texel: UNORM floats + its contribution texel*255 to the mean's running sum
+// (ASTC_Encode.hlsl:142-147, 565-580).  Linear: RN(raw*255) == c exactly for every
+// byte, so the sum adds the byte values themselves.  sRGB: rgb come from the LUT
+// and the product is rounded (scalar FMUL) before the add; alpha is never
+// sRGB-decoded.  NORMAL: b = a = 1.0 (:575-578), handled by the caller as constants.
+template <bool SRGB, bool NORMAL>
+__device__ __forceinline__ Texel convert_texel(uint32_t w, const float *lut_rgb, f2 &sum_lo, f2 &sum_hi)
 {
-    float4 r;
-    if (SRGB) {
-        r.x = lut_rgb[w & 0xFFu];
-        r.y = lut_rgb[(w >> 8) & 0xFFu];
-        r.z = lut_rgb[(w >> 16) & 0xFFu];
+    Texel t;
+    if (!SRGB) {
+        const f2 clo = bytes_lo(w);
+        t.lo = unorm2(clo);
+        sum_lo = dev::add2(sum_lo, clo);
+        if (!NORMAL) {
+            const f2 chi = bytes_hi(w);
+            t.hi = unorm2(chi);
+            sum_hi = dev::add2(sum_hi, chi);
+        }
     } else {
-        r.x = unorm_linear(byte_to_float<0>(w));
-        r.y = unorm_linear(byte_to_float<1>(w));
-        r.z = unorm_linear(byte_to_float<2>(w));
+        t.lo = dev::mk(lut_rgb[w & 0xFFu], lut_rgb[(w >> 8) & 0xFFu]);
+        sum_lo = dev::add2(sum_lo, dev::mk(dev::fmul(t.lo.x, 255.0f), dev::fmul(t.lo.y, 255.0f)));
+        if (!NORMAL) {
+            const float ca = dev::fsub(byte_bits<3>(w), 8388608.0f);
+            t.hi = dev::mk(lut_rgb[(w >> 16) & 0xFFu], unorm1(ca));
+            sum_hi = dev::add2(sum_hi, dev::mk(dev::fmul(t.hi.x, 255.0f), ca));
+        }
     }
-    r.w = unorm_linear(byte_to_float<3>(w));          // alpha is never sRGB-decoded
-    return r;
+    if (NORMAL) t.hi = dev::bc(1.0f);
+    return t;
 }
 
 // ---------------------------------------------------------------------------
@@ -118,71 +137,199 @@ __device__ __forceinline__ bool locate(const EncodeParams &p, uint64_t id, Locat
     return true;
 }
 
-template <bool ALPHA>
-__device__ __forceinline__ void load_shared_tables(uint32_t *trit_scattered)
+template <bool ALPHA, bool SRGB>
+__device__ __forceinline__ void load_shared_tables(dev::SharedTables &st)
 {
-    const TritScatter &src = ALPHA ? c_trit_scatter_q6 : c_trit_scatter_q12;
-    for (int i = threadIdx.x; i < 243; i += blockDim.x) trit_scattered[i] = src.v[i];
+    const dev::TableImage &src = ALPHA ? c_tables_q6 : c_tables_q12;
+    for (int i = threadIdx.x; i < 5 * dev::kFieldStride; i += blockDim.x) st.field[i] = src.field[i];
+    for (int i = threadIdx.x; i < 244; i += blockDim.x) st.trit_scattered[i] = src.trit_scattered[i];
+    if (SRGB) for (int i = threadIdx.x; i < 256; i += blockDim.x) st.lut_rgb[i] = c_srgb_lut[i];
 }
 
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return uint32_t(__cvta_generic_to_shared(p)); }
+
 // ---------------------------------------------------------------------------
-// 4x4: sixteen texels live in registers as UNORM floats.
+// 4x4: sixteen texels live in registers as UNORM float pairs.
 // ---------------------------------------------------------------------------
 struct Texels4x4 {
-    float4 t[16];
-    __device__ __forceinline__ float4 raw(int k) const { return t[k]; }
+    Texel t[16];
+    __device__ __forceinline__ Texel raw(int k) const { return t[k]; }
     __device__ __forceinline__ void fence() const {}
 };
 
-constexpr int kThreads4x4 = 128;
+#ifndef ASTC_THREADS_4X4
+#define ASTC_THREADS_4X4 128
+#endif
+#ifndef ASTC_MINBLOCKS_4X4
+#define ASTC_MINBLOCKS_4X4 3
+#endif
+constexpr int kThreads4x4 = ASTC_THREADS_4X4;
+
+#ifndef ASTC_PREFETCH_4X4
+#define ASTC_PREFETCH_4X4 1
+#endif
+#ifndef ASTC_BPT_4X4
+#define ASTC_BPT_4X4 8
+#endif
+constexpr int kBlocksPerThread4x4 = ASTC_BPT_4X4;   // ASTC blocks each thread encodes, one after the other
+
+// The four 16-byte texel rows of an interior block, fetched one block ahead of use.
+struct Rows4x4 {
+    uint4 r[4];
+    bool fast;
+};
+
+__device__ __forceinline__ void fetch_rows(const Located &loc, Rows4x4 &rows)
+{
+    const int x0 = loc.bx * 4, y0 = loc.by * 4;
+    rows.fast = (loc.flags & kFlagAligned16) && x0 + 4 <= loc.width && y0 + 4 <= loc.height;
+    if (rows.fast) {
+        // one 16-byte read-only load per texel row; adjacent threads read adjacent
+        // 16 B, i.e. 512 contiguous bytes per warp per row.
+        const uint8_t *base = loc.rgba + size_t(y0) * loc.pitch + size_t(x0) * 4u;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) rows.r[r] = __ldg((const uint4 *)(base + size_t(r) * loc.pitch));
+    }
+}
 
 template <bool ALPHA, bool NORMAL, bool SRGB, bool BATCH>
-__global__ void __launch_bounds__(kThreads4x4)
+__global__ void __launch_bounds__(kThreads4x4, ASTC_MINBLOCKS_4X4)
 encode4x4_kernel(const EncodeParams p)
 {
-    __shared__ uint32_t s_trit[243];
-    __shared__ float s_lut[SRGB ? 256 : 1];
-    load_shared_tables<ALPHA>(s_trit);
-    if (SRGB) for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = c_srgb_lut[i];
+    __shared__ dev::SharedTables st;
+    load_shared_tables<ALPHA, SRGB>(st);
     __syncthreads();
+    const uint32_t s_field = smem_addr(st.field), s_trit = smem_addr(st.trit_scattered);
 
-    const uint64_t id = uint64_t(blockIdx.x) * kThreads4x4 + threadIdx.x;
+    // CTA b owns ids [b*BPT*T, (b+1)*BPT*T); pass i takes the i-th run of T consecutive ids, so a
+    // warp still reads 512 contiguous bytes per texel row and stores 512 contiguous bytes.
+    uint64_t id = uint64_t(blockIdx.x) * (kBlocksPerThread4x4 * kThreads4x4) + threadIdx.x;
     Located loc;
-    if (!locate<BATCH>(p, id, loc)) return;
-
-    Texels4x4 tx;
-    const int x0 = loc.bx * 4, y0 = loc.by * 4;
-    const uint8_t *base = loc.rgba + size_t(y0) * loc.pitch + size_t(x0) * 4u;
-    if ((loc.flags & kFlagAligned16) && x0 + 4 <= loc.width && y0 + 4 <= loc.height) {
-        // interior: one 16-byte read-only load per texel row; adjacent threads
-        // read adjacent 16 B, i.e. 512 contiguous bytes per warp per row.
-        uint4 rows[4];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) rows[r] = __ldg((const uint4 *)(base + size_t(r) * loc.pitch));
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            tx.t[4 * r + 0] = unorm_texel<SRGB>(rows[r].x, s_lut);
-            tx.t[4 * r + 1] = unorm_texel<SRGB>(rows[r].y, s_lut);
-            tx.t[4 * r + 2] = unorm_texel<SRGB>(rows[r].z, s_lut);
-            tx.t[4 * r + 3] = unorm_texel<SRGB>(rows[r].w, s_lut);
+    Rows4x4 rows;
+    bool valid = locate<BATCH>(p, id, loc);
+    if (valid) fetch_rows(loc, rows);
+#pragma unroll 1
+    for (int pass = 0; pass < kBlocksPerThread4x4 && valid; ++pass) {
+        const Located cur = loc;
+        const Rows4x4 now = rows;
+#if ASTC_PREFETCH_4X4
+        if (pass + 1 < kBlocksPerThread4x4) {              // software prefetch: next block's rows in flight during this encode
+            id += kThreads4x4;
+            valid = locate<BATCH>(p, id, loc);
+            if (valid) fetch_rows(loc, rows);
         }
-    } else {
-        // edge / unaligned: per-texel loads, out-of-range texels read as 0
-        // like Texture2D.Load (ASTC_Encode.hlsl:574).
+#endif
+        Texels4x4 tx;
+        f2 sum_lo = dev::bc(0.f), sum_hi = dev::bc(0.f);
+        if (now.fast) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const int x = x0 + (k & 3), y = y0 + (k >> 2);
-            const bool inside = x < loc.width && y < loc.height;
-            const uint32_t w = inside ? __ldg((const uint32_t *)(base + size_t(k >> 2) * loc.pitch + size_t(k & 3) * 4u)) : 0u;
-            tx.t[k] = inside ? unorm_texel<SRGB>(w, s_lut) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int r = 0; r < 4; ++r) {
+                tx.t[4 * r + 0] = convert_texel<SRGB, NORMAL>(now.r[r].x, st.lut_rgb, sum_lo, sum_hi);
+                tx.t[4 * r + 1] = convert_texel<SRGB, NORMAL>(now.r[r].y, st.lut_rgb, sum_lo, sum_hi);
+                tx.t[4 * r + 2] = convert_texel<SRGB, NORMAL>(now.r[r].z, st.lut_rgb, sum_lo, sum_hi);
+                tx.t[4 * r + 3] = convert_texel<SRGB, NORMAL>(now.r[r].w, st.lut_rgb, sum_lo, sum_hi);
+            }
+        } else {
+            // edge / unaligned: per-texel loads, out-of-range texels read as 0
+            // like Texture2D.Load (ASTC_Encode.hlsl:574); the UNORM / sRGB value of byte 0 is 0.
+            const int x0 = cur.bx * 4, y0 = cur.by * 4;
+            const uint8_t *base = cur.rgba + size_t(y0) * cur.pitch + size_t(x0) * 4u;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const int x = x0 + (k & 3), y = y0 + (k >> 2);
+                const bool inside = x < cur.width && y < cur.height;
+                const uint32_t w = inside ? __ldg((const uint32_t *)(base + size_t(k >> 2) * cur.pitch + size_t(k & 3) * 4u)) : 0u;
+                tx.t[k] = convert_texel<SRGB, NORMAL>(w, st.lut_rgb, sum_lo, sum_hi);
+            }
         }
+        // one coalesced 16-byte store per thread
+        *cur.out = dev::encode_block<4, ALPHA, NORMAL>(tx, sum_lo, sum_hi, s_field, s_trit);
+#if !ASTC_PREFETCH_4X4
+        if (pass + 1 < kBlocksPerThread4x4) {
+            id += kThreads4x4;
+            valid = locate<BATCH>(p, id, loc);
+            if (valid) fetch_rows(loc, rows);
+        }
+#endif
     }
-    if (NORMAL) {                                         // ASTC_Encode.hlsl:575-578
-#pragma unroll
-        for (int k = 0; k < 16; ++k) { tx.t[k].z = 1.0f; tx.t[k].w = 1.0f; }
-    }
-    *loc.out = dev::encode_block<4, ALPHA>(tx, s_trit);   // one coalesced 16-byte store per thread
 }
+
+#if ASTC_4X4_SMEM
+// ---------------------------------------------------------------------------
+// 4x4 experiment: texels parked in shared memory (as the 6x6 path does) to free
+// registers for occupancy.
+// ---------------------------------------------------------------------------
+#ifndef ASTC_THREADS_4X4S
+#define ASTC_THREADS_4X4S 128
+#endif
+#ifndef ASTC_MINBLOCKS_4X4S
+#define ASTC_MINBLOCKS_4X4S 5
+#endif
+constexpr int kThreads4x4S = ASTC_THREADS_4X4S;
+
+struct Texels4x4S {
+    const float4 *col;
+    __device__ __forceinline__ Texel raw(int k) const
+    {
+        const float4 v = col[k * kThreads4x4S];
+        return Texel{dev::mk(v.x, v.y), dev::mk(v.z, v.w)};
+    }
+    __device__ __forceinline__ void fence() const { asm volatile("" ::: "memory"); }
+};
+
+template <bool ALPHA, bool NORMAL, bool SRGB, bool BATCH>
+__global__ void __launch_bounds__(kThreads4x4S, ASTC_MINBLOCKS_4X4S)
+encode4x4s_kernel(const EncodeParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4 *s_tex = reinterpret_cast<float4 *>(smem_raw);                   // [16][kThreads4x4S]
+    dev::SharedTables &st = *reinterpret_cast<dev::SharedTables *>(s_tex + 16 * kThreads4x4S);
+    load_shared_tables<ALPHA, SRGB>(st);
+    __syncthreads();
+    const uint32_t s_field = smem_addr(st.field), s_trit = smem_addr(st.trit_scattered);
+    float4 *col = s_tex + threadIdx.x;
+
+    uint64_t id = uint64_t(blockIdx.x) * (kBlocksPerThread4x4 * kThreads4x4S) + threadIdx.x;
+    Located loc;
+    Rows4x4 rows;
+    bool valid = locate<BATCH>(p, id, loc);
+    if (valid) fetch_rows(loc, rows);
+#pragma unroll 1
+    for (int pass = 0; pass < kBlocksPerThread4x4 && valid; ++pass) {
+        const Located cur = loc;
+        const Rows4x4 now = rows;
+        f2 sum_lo = dev::bc(0.f), sum_hi = dev::bc(0.f);
+        auto park = [&](int k, uint32_t w) {
+            const Texel t = convert_texel<SRGB, NORMAL>(w, st.lut_rgb, sum_lo, sum_hi);
+            col[k * kThreads4x4S] = make_float4(t.lo.x, t.lo.y, t.hi.x, t.hi.y);
+        };
+        if (now.fast) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                park(4 * r + 0, now.r[r].x); park(4 * r + 1, now.r[r].y);
+                park(4 * r + 2, now.r[r].z); park(4 * r + 3, now.r[r].w);
+            }
+        } else {
+            const int x0 = cur.bx * 4, y0 = cur.by * 4;
+            const uint8_t *base = cur.rgba + size_t(y0) * cur.pitch + size_t(x0) * 4u;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const int x = x0 + (k & 3), y = y0 + (k >> 2);
+                const bool inside = x < cur.width && y < cur.height;
+                park(k, inside ? __ldg((const uint32_t *)(base + size_t(k >> 2) * cur.pitch + size_t(k & 3) * 4u)) : 0u);
+            }
+        }
+        if (pass + 1 < kBlocksPerThread4x4) {              // next block's rows in flight during this encode
+            id += kThreads4x4S;
+            valid = locate<BATCH>(p, id, loc);
+            if (valid) fetch_rows(loc, rows);
+        }
+        Texels4x4S tx{col};
+        *cur.out = dev::encode_block<4, ALPHA, NORMAL>(tx, sum_lo, sum_hi, s_field, s_trit);
+    }
+}
+constexpr size_t kSmem4x4S = size_t(16) * kThreads4x4S * sizeof(float4) + sizeof(dev::SharedTables);
+#endif
 
 // ---------------------------------------------------------------------------
 // 6x6: 36 texels do not fit registers as floats; each thread parks its block
@@ -192,7 +339,11 @@ constexpr int kThreads6x6 = 128;
 
 struct Texels6x6 {
     const float4 *col;                                    // &smem[threadIdx.x], stride kThreads6x6
-    __device__ __forceinline__ float4 raw(int k) const { return col[k * kThreads6x6]; }
+    __device__ __forceinline__ Texel raw(int k) const
+    {
+        const float4 v = col[k * kThreads6x6];
+        return Texel{dev::mk(v.x, v.y), dev::mk(v.z, v.w)};
+    }
     __device__ __forceinline__ void fence() const { asm volatile("" ::: "memory"); }
 };
 
@@ -202,10 +353,8 @@ encode6x6_kernel(const EncodeParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *s_tex = reinterpret_cast<float4 *>(smem_raw);                   // [36][kThreads6x6]
-    uint32_t *s_trit = reinterpret_cast<uint32_t *>(s_tex + 36 * kThreads6x6);
-    float *s_lut = reinterpret_cast<float *>(s_trit + 244);
-    load_shared_tables<ALPHA>(s_trit);
-    if (SRGB) for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = c_srgb_lut[i];
+    dev::SharedTables &st = *reinterpret_cast<dev::SharedTables *>(s_tex + 36 * kThreads6x6);
+    load_shared_tables<ALPHA, SRGB>(st);
     __syncthreads();
 
     const uint64_t id = uint64_t(blockIdx.x) * kThreads6x6 + threadIdx.x;
@@ -213,8 +362,13 @@ encode6x6_kernel(const EncodeParams p)
     if (!locate<BATCH>(p, id, loc)) return;
 
     float4 *col = s_tex + threadIdx.x;
+    f2 sum_lo = dev::bc(0.f), sum_hi = dev::bc(0.f);
     const int x0 = loc.bx * 6, y0 = loc.by * 6;
     const uint8_t *base = loc.rgba + size_t(y0) * loc.pitch + size_t(x0) * 4u;
+    auto park = [&](int k, uint32_t w) {
+        const Texel t = convert_texel<SRGB, NORMAL>(w, st.lut_rgb, sum_lo, sum_hi);
+        col[k * kThreads6x6] = make_float4(t.lo.x, t.lo.y, t.hi.x, t.hi.y);
+    };
     if ((loc.flags & kFlagAligned8) && x0 + 6 <= loc.width && y0 + 6 <= loc.height) {
         // interior: a block row is 24 B = three 8-byte loads; a warp covers 768
         // contiguous bytes per texel row.
@@ -222,36 +376,25 @@ encode6x6_kernel(const EncodeParams p)
         for (int r = 0; r < 6; ++r) {
             const uint2 *src = (const uint2 *)(base + size_t(r) * loc.pitch);
             const uint2 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
-            col[(6 * r + 0) * kThreads6x6] = unorm_texel<SRGB>(a.x, s_lut);
-            col[(6 * r + 1) * kThreads6x6] = unorm_texel<SRGB>(a.y, s_lut);
-            col[(6 * r + 2) * kThreads6x6] = unorm_texel<SRGB>(b.x, s_lut);
-            col[(6 * r + 3) * kThreads6x6] = unorm_texel<SRGB>(b.y, s_lut);
-            col[(6 * r + 4) * kThreads6x6] = unorm_texel<SRGB>(c.x, s_lut);
-            col[(6 * r + 5) * kThreads6x6] = unorm_texel<SRGB>(c.y, s_lut);
+            park(6 * r + 0, a.x); park(6 * r + 1, a.y);
+            park(6 * r + 2, b.x); park(6 * r + 3, b.y);
+            park(6 * r + 4, c.x); park(6 * r + 5, c.y);
         }
     } else {
 #pragma unroll 6
         for (int k = 0; k < 36; ++k) {
             const int kx = k % 6, ky = k / 6;
             const bool inside = x0 + kx < loc.width && y0 + ky < loc.height;
-            const uint32_t w = inside ? __ldg((const uint32_t *)(base + size_t(ky) * loc.pitch + size_t(kx) * 4u)) : 0u;
-            col[k * kThreads6x6] = inside ? unorm_texel<SRGB>(w, s_lut) : make_float4(0.f, 0.f, 0.f, 0.f);
+            park(k, inside ? __ldg((const uint32_t *)(base + size_t(ky) * loc.pitch + size_t(kx) * 4u)) : 0u);
         }
     }
-    if (NORMAL) {
-#pragma unroll 6
-        for (int k = 0; k < 36; ++k) {
-            float4 v = col[k * kThreads6x6];
-            v.z = 1.0f; v.w = 1.0f;
-            col[k * kThreads6x6] = v;
-        }
-    }
+    if (NORMAL) sum_hi = dev::bc(36.0f * 255.0f);
     // each thread reads back only its own column: no barrier needed
     Texels6x6 tx{col};
-    *loc.out = dev::encode_block<6, ALPHA>(tx, s_trit);
+    *loc.out = dev::encode_block<6, ALPHA, NORMAL>(tx, sum_lo, sum_hi, smem_addr(st.field), smem_addr(st.trit_scattered));
 }
 
-constexpr size_t kSmem6x6 = size_t(36) * kThreads6x6 * sizeof(float4) + 244 * sizeof(uint32_t) + 256 * sizeof(float);
+constexpr size_t kSmem6x6 = size_t(36) * kThreads6x6 * sizeof(float4) + sizeof(dev::SharedTables);
 
 // ---------------------------------------------------------------------------
 // launch
@@ -260,9 +403,20 @@ template <bool ALPHA, bool NORMAL, bool SRGB, bool BATCH>
 static cudaError_t launch_variant(int dim, const EncodeParams &p, cudaStream_t stream)
 {
     if (dim == 4) {
-        const uint64_t ctas = (p.total_blocks + kThreads4x4 - 1) / kThreads4x4;
+#if ASTC_4X4_SMEM
+        constexpr uint64_t per_cta = uint64_t(kThreads4x4S) * kBlocksPerThread4x4;
+        const uint64_t ctas = (p.total_blocks + per_cta - 1) / per_cta;
+        if (ctas > 0x7FFFFFFFull) return cudaErrorInvalidConfiguration;
+        auto kern = encode4x4s_kernel<ALPHA, NORMAL, SRGB, BATCH>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmem4x4S));
+        if (e != cudaSuccess) return e;
+        kern<<<unsigned(ctas), kThreads4x4S, kSmem4x4S, stream>>>(p);
+#else
+        constexpr uint64_t per_cta = uint64_t(kThreads4x4) * kBlocksPerThread4x4;
+        const uint64_t ctas = (p.total_blocks + per_cta - 1) / per_cta;
         if (ctas > 0x7FFFFFFFull) return cudaErrorInvalidConfiguration;
         encode4x4_kernel<ALPHA, NORMAL, SRGB, BATCH><<<unsigned(ctas), kThreads4x4, 0, stream>>>(p);
+#endif
     } else {
         const uint64_t ctas = (p.total_blocks + kThreads6x6 - 1) / kThreads6x6;
         if (ctas > 0x7FFFFFFFull) return cudaErrorInvalidConfiguration;

@@ -22,6 +22,11 @@ def run(w, h, opt, label, iters=10):
     print(f"{label}: {w}x{h} median {med:.3f} ms best {ts[0]:.3f} ms -> {w*h/med/1e6:.1f} Gtexel/s", flush=True)
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "short":
+        run(16384, 16384, A.encode_option(), "4x4 rgb")
+        run(4096, 4096, A.encode_option(has_alpha=True), "4x4 rgba")
+        run(8192, 8192, A.encode_option(is6x6=True, has_alpha=True, srgb=True), "6x6 rgba srgb")
+        sys.exit(0)
     print(A.version(), torch.cuda.get_device_name(0))
     run(4096, 4096, A.encode_option(), "4x4 rgb")
     run(4096, 4096, A.encode_option(has_alpha=True), "4x4 rgba")
