@@ -240,14 +240,15 @@ def encode_astc_host(rgba: np.ndarray, option: encode_option, out: Optional[np.n
                      srgb_texture: Optional[bool] = None) -> np.ndarray:
     """Upload + encode + read-back in one synchronous call on host memory
     (load_tex's upload + encode_astc + read_gpu).  rgba: (H, W, 4) uint8."""
-    if rgba.dtype != np.uint8 or rgba.ndim != 3 or rgba.shape[2] != 4 or rgba.strides[2] != 1 or rgba.strides[1] != 4:
+    if rgba.dtype != np.uint8 or rgba.ndim != 3 or rgba.shape[2] != 4 or \
+            (rgba.size and (rgba.strides[2] != 1 or rgba.strides[1] != 4)):
         raise ValueError("rgba must be a uint8 array of shape (H, W, 4) with packed texels")
     h, w = rgba.shape[:2]
     o = _effective(option, srgb_texture)
     nbytes = int(lib().astc_b200_output_size(w, h, C.byref(o)))
     if out is None:
         out = np.empty((nbytes // BLOCK_BYTES, BLOCK_BYTES), dtype=np.uint8)
-    pitch = rgba.strides[0] if h > 1 else w * 4
+    pitch = rgba.strides[0] if (h > 1 and rgba.size) else w * 4
     _check(lib().astc_b200_encode_host(rgba.ctypes.data, w, h, pitch, C.byref(o), out.ctypes.data), "encode_astc_host")
     return out
 

@@ -72,6 +72,7 @@ def build_variant(tag: str, defines, verbose: bool = False) -> Path:
             _run([nvcc, "-ccbin", _host_cxx(), *NVCC_FLAGS, "-c", CSRC / src, "-o", obj], verbose)
         objs.append(obj)
     _run([nvcc, "-ccbin", _host_cxx(), "-shared", "-o", lib, *objs, "-lz"], verbose)
+    kobj.unlink()
     return lib
 
 

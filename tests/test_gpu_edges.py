@@ -1,0 +1,159 @@
+"""CUDA path edge cases and API surface, all through the C ABI, all bit-exact vs the oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _enc(native, img_t, opt, **kw):
+    import torch
+    out = native.encode_astc(img_t, opt, **kw)
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+def _okw(opt, dim):
+    return dict(block_dim=dim, has_alpha=opt.has_alpha, is_normal_map=opt.is_normal_map, srgb=opt.srgb)
+
+
+@pytest.mark.parametrize("dim", [4, 6])
+@pytest.mark.parametrize("size", [(1, 1), (2, 2), (3, 5), (4, 4), (6, 6), (7, 1), (1, 9), (129, 3), (16, 4097)], ids=str)
+def test_tiny_and_ragged_sizes(native, oracle, dim, size):
+    import torch
+    w, h = size
+    rng = np.random.default_rng(w * 131 + h)
+    img = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+    for opt in (native.encode_option(is4x4=dim == 4, is6x6=dim == 6),
+                native.encode_option(is4x4=dim == 4, is6x6=dim == 6, has_alpha=True, srgb=True),
+                native.encode_option(is4x4=dim == 4, is6x6=dim == 6, is_normal_map=True)):
+        got = _enc(native, torch.from_numpy(img).cuda(), opt)
+        want = oracle.encode_image(img, **_okw(opt, dim))
+        assert np.array_equal(got, want), (size, opt)
+
+
+@pytest.mark.parametrize("dim", [4, 6])
+def test_special_content(native, oracle, dim):
+    """Flat, alpha-only variation (4-D PCA quirk), saturated, two-tone, single-channel ramps."""
+    import torch
+    rng = np.random.default_rng(11)
+    n = 64
+    tiles = []
+    flat = np.zeros((dim, dim * n, 4), np.uint8); flat[:] = rng.integers(0, 256, (1, n, 1, 4)).repeat(dim, 2).reshape(1, dim * n, 4)
+    tiles.append(flat)
+    aonly = flat.copy(); aonly[..., 3] = rng.integers(0, 256, (dim, dim * n)); tiles.append(aonly)
+    sat = rng.choice(np.array([0, 255], np.uint8), (dim, dim * n, 4)); tiles.append(sat)
+    two = np.where(rng.random((dim, dim * n, 1)) < 0.5, rng.integers(0, 256, 4), rng.integers(0, 256, 4)).astype(np.uint8); tiles.append(two)
+    ramp = np.zeros((dim, dim * n, 4), np.uint8); ramp[..., 1] = (np.arange(dim * n) * 3) % 256; ramp[..., 3] = 255; tiles.append(ramp)
+    near = np.full((dim, dim * n, 4), 100, np.uint8); near[::2, ::3, 0] = 101; tiles.append(near)
+    img = np.concatenate(tiles, axis=0)
+    for kw in (dict(), dict(has_alpha=True), dict(srgb=True), dict(has_alpha=True, srgb=True), dict(is_normal_map=True)):
+        opt = native.encode_option(is4x4=dim == 4, is6x6=dim == 6, **kw)
+        got = _enc(native, torch.from_numpy(img).cuda(), opt)
+        want = oracle.encode_image(img, **_okw(opt, dim))
+        bad = np.nonzero((got != want).any(axis=1))[0]
+        assert len(bad) == 0, (kw, bad[:10])
+
+
+@pytest.mark.parametrize("dim", [4, 6])
+def test_pitch_and_unaligned_base(native, oracle, dim):
+    """Row pitch larger than the width, and a base pointer that is only 4-byte aligned (slow path)."""
+    import torch
+    from astc_encoder_b200 import synth
+    big = synth.synth_rgba(300, 200, 5).cuda()
+    opt = native.encode_option(is4x4=dim == 4, is6x6=dim == 6, has_alpha=True)
+    for x0, w in ((0, 256), (1, 255), (3, 250), (4, 96)):
+        view = big[10:170, x0:x0 + w]                       # strided rows, base offset 4*x0 bytes
+        got = _enc(native, view, opt)
+        want = oracle.encode_image(view.cpu().numpy(), **_okw(opt, dim))
+        assert np.array_equal(got, want), (x0, w)
+
+
+def test_explicit_out_and_stream(native, oracle):
+    import torch
+    from astc_encoder_b200 import synth
+    img = synth.synth_rgba(128, 64, 6).cuda()
+    opt = native.encode_option(has_alpha=True)
+    out = torch.zeros((native.output_size(128, 64, opt) // 16, 16), dtype=torch.uint8, device="cuda")
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        native.encode_astc(img, opt, out=out, stream=s)
+    s.synchronize()
+    assert np.array_equal(out.cpu().numpy(), oracle.encode_image(img.cpu().numpy(), block_dim=4, has_alpha=True))
+    with pytest.raises(ValueError):
+        native.encode_astc(img.cpu(), opt)
+    with pytest.raises(ValueError):
+        native.encode_astc(img, opt, out=out[:10])
+
+
+def test_srgb_texture_override(native, oracle):
+    """encode_astc's texture format decides sRGB decoding (main.cpp:38,214), not the option flag."""
+    import torch
+    from astc_encoder_b200 import synth
+    img = synth.synth_rgba(64, 64, 7)
+    opt = native.encode_option(srgb=True)
+    lin = _enc(native, img.cuda(), opt, srgb_texture=False)
+    assert np.array_equal(lin, oracle.encode_image(img.numpy(), block_dim=4))
+    srgb = _enc(native, img.cuda(), native.encode_option(), srgb_texture=True)
+    assert np.array_equal(srgb, oracle.encode_image(img.numpy(), block_dim=4, srgb=True))
+
+
+@pytest.mark.parametrize("dim", [4, 6])
+def test_batch_of_mip_chains_one_launch(native, oracle, dim):
+    import torch
+    from astc_encoder_b200 import synth
+    chains = [synth.mip_chain(synth.synth_rgba(64, 64, synth.SEED_BATCH + i).cuda()) for i in range(3)]
+    srcs = [m for c in chains for m in c]
+    assert [tuple(m.shape[:2]) for m in chains[0]] == [(64 >> i, 64 >> i) for i in range(7)]
+    opt = native.encode_option(is4x4=dim == 4, is6x6=dim == 6, has_alpha=True)
+    before = native.launch_count()
+    batch = native.Batch(srcs, opt)
+    outs = batch.encode()
+    torch.cuda.synchronize()
+    assert native.launch_count() - before == 1
+    assert batch.total_texels == sum(m.shape[0] * m.shape[1] for m in srcs)
+    for m, o in zip(srcs, outs):
+        want = oracle.encode_image(m.cpu().numpy(), **_okw(opt, dim))
+        assert np.array_equal(o.cpu().numpy(), want), tuple(m.shape)
+    batch.close()
+    empty = native.Batch([], opt)
+    empty.encode()
+    assert empty.total_blocks == 0
+
+
+def test_host_entry_point_matches_device_path(native, oracle):
+    from astc_encoder_b200 import synth
+    img = synth.synth_rgba(1000, 3000, 8).numpy()              # several internal bands
+    for dim, kw in ((4, dict()), (6, dict(has_alpha=True, srgb=True))):
+        opt = native.encode_option(is4x4=dim == 4, is6x6=dim == 6, **kw)
+        got = native.encode_astc_host(img, opt)
+        assert np.array_equal(got, oracle.encode_image(img, block_dim=dim, **kw))
+    assert native.encode_astc_host(np.zeros((0, 8, 4), np.uint8), native.encode_option()).shape == (0, 16)
+
+
+def test_device_decoder_matches_oracle_decoder(native, oracle):
+    import torch
+    from astc_encoder_b200 import synth
+    img = synth.synth_rgba(250, 187, 9)
+    for dim, kw in ((4, dict(has_alpha=True)), (4, dict()), (6, dict(has_alpha=True)), (6, dict())):
+        opt = native.encode_option(is4x4=dim == 4, is6x6=dim == 6, **kw)
+        blocks = native.encode_astc(img.cuda(), opt)
+        dec = native.decode_astc(blocks, 250, 187, dim).cpu().numpy()
+        ref, bad = oracle.decode_image(blocks.cpu().numpy(), 250, 187, dim)
+        assert bad == 0 and np.array_equal(dec, ref)
+
+
+def test_leaf_srgb_alpha_config0(native, oracle, leaf_rgba):
+    """BASELINE config[0] as written (`leaf.png -alpha -4x4 -srgb`): only the oracle can check it."""
+    import torch
+    opt = native.encode_option(has_alpha=True, srgb=True)
+    got = _enc(native, torch.from_numpy(leaf_rgba).cuda(), opt)
+    assert np.array_equal(got, oracle.encode_image(leaf_rgba, block_dim=4, has_alpha=True, srgb=True))
+
+
+def test_leaf_psnr_vs_golden(native, oracle, leaf_rgba, leaf_golden):
+    import torch
+    got = _enc(native, torch.from_numpy(leaf_rgba).cuda(), native.encode_option(has_alpha=True))
+    dec = native.decode_astc(torch.from_numpy(got).cuda(), 1024, 1024, 4).cpu().numpy()
+    dec_g, _ = oracle.decode_image(leaf_golden[4], 1024, 1024, 4)
+    p, pg = oracle.psnr_per_channel(dec, leaf_rgba), oracle.psnr_per_channel(dec_g, leaf_rgba)
+    assert np.all(np.abs(p - pg) <= 0.05), (p, pg)
