@@ -146,12 +146,13 @@ def run_reference(args) -> int:
     O.lib()
     rows_texels = 1024                                           # 16384 x 1024 texels per step
     img = synth.synth_rgba(W16K, rows_texels, synth.SEED_CFG5).numpy()
-    threads = os.cpu_count() or 1
+    # all host threads this process may run on -- explicitly, because torchrun exports OMP_NUM_THREADS=1
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     for _ in range(max(1, args.warmup)):
-        _, used = O.encode_rows(img, 0, rows_texels // 4, block_dim=4, threads=0)
+        _, used = O.encode_rows(img, 0, rows_texels // 4, block_dim=4, threads=threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        _, used = O.encode_rows(img, 0, rows_texels // 4, block_dim=4, threads=0)
+        _, used = O.encode_rows(img, 0, rows_texels // 4, block_dim=4, threads=threads)
     dt = (time.perf_counter() - t0) / args.steps
     value = W16K * rows_texels / dt / 1e6
     sample = f"block rows 0..{rows_texels // 4 - 1} ({W16K}x{rows_texels} texels) of the 16384x16384 texture per step"
@@ -311,7 +312,8 @@ def run_b200(args) -> int:
         rows_texels = 4096
         sample = tex[:rows_texels].cpu().numpy()
         t0 = time.perf_counter()
-        want, used = O.encode_rows(sample, 0, rows_texels // 4, block_dim=4, threads=0)
+        ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        want, used = O.encode_rows(sample, 0, rows_texels // 4, block_dim=4, threads=ncpu)
         dt = time.perf_counter() - t0
         got = out[: want.shape[0]].cpu().numpy()
         same = int((got == want).all(axis=1).sum())
