@@ -8,6 +8,8 @@
 
 #include <cuda_runtime.h>
 
+#include <cstddef>
+
 #include "astc_block.cuh"
 
 namespace astc {
@@ -15,8 +17,11 @@ namespace astc {
 // ---------------------------------------------------------------------------
 // constant tables
 // ---------------------------------------------------------------------------
-__constant__ dev::TableImage c_tables_q6 = dev::make_table_image<QUANT_6>();
-__constant__ dev::TableImage c_tables_q12 = dev::make_table_image<QUANT_12>();
+// Encoder tables live in global memory (L2-resident after the first CTA) and are copied to
+// shared memory with coalesced 16-byte loads; a per-thread-indexed __constant__ read would
+// serialise 32 ways.
+__device__ const dev::TableImage g_tables_q6 = dev::make_table_image<QUANT_6>();
+__device__ const dev::TableImage g_tables_q12 = dev::make_table_image<QUANT_12>();
 __constant__ TritPack c_trit_pack = make_trit_pack();
 __constant__ QuintPack c_quint_pack = make_quint_pack();
 __constant__ WeightTables c_weight_tables = make_weight_tables();
@@ -24,9 +29,9 @@ __constant__ WeightTables c_weight_tables = make_weight_tables();
 static const float h_srgb_lut[256] = {
 #include "srgb_lut.inc"
 };
-__constant__ float c_srgb_lut[256] = {
+__device__ const dev::LutImage g_srgb_lut = {{
 #include "srgb_lut.inc"
-};
+}};
 
 const float *host_srgb_lut() { return h_srgb_lut; }
 
@@ -68,6 +73,16 @@ __device__ __forceinline__ f2 bytes_hi(uint32_t w)
     return dev::add2(dev::mk(byte_bits<2>(w), byte_bits<3>(w)), dev::bc(-8388608.0f));
 }
 
+// sRGB LUT entry of byte SEL: one PRMT (zero-extended byte), one IMAD for the address, one LDS.
+template <int SEL>
+__device__ __forceinline__ float lut_at(const float *lut_rgb, uint32_t w)
+{
+    const uint32_t b = __byte_perm(w, 0u, 0x4440 | SEL);
+    float v;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(b * 4u + uint32_t(__cvta_generic_to_shared(lut_rgb))));
+    return v;
+}
+
 // One texel: UNORM floats + its contribution texel*255 to the mean's running sum
 // (ASTC_Encode.hlsl:142-147, 565-580).  Linear: RN(raw*255) == c exactly for every
 // byte, so the sum adds the byte values themselves.  sRGB: rgb come from the LUT
@@ -87,11 +102,11 @@ __device__ __forceinline__ Texel convert_texel(uint32_t w, const float *lut_rgb,
             sum_hi = dev::add2(sum_hi, chi);
         }
     } else {
-        t.lo = dev::mk(lut_rgb[w & 0xFFu], lut_rgb[(w >> 8) & 0xFFu]);
+        t.lo = dev::mk(lut_at<0>(lut_rgb, w), lut_at<1>(lut_rgb, w));
         sum_lo = dev::add2(sum_lo, dev::mk(dev::fmul(t.lo.x, 255.0f), dev::fmul(t.lo.y, 255.0f)));
         if (!NORMAL) {
             const float ca = dev::fsub(byte_bits<3>(w), 8388608.0f);
-            t.hi = dev::mk(lut_rgb[(w >> 16) & 0xFFu], unorm1(ca));
+            t.hi = dev::mk(lut_at<2>(lut_rgb, w), unorm1(ca));
             sum_hi = dev::add2(sum_hi, dev::mk(dev::fmul(t.hi.x, 255.0f), ca));
         }
     }
@@ -140,10 +155,15 @@ __device__ __forceinline__ bool locate(const EncodeParams &p, uint64_t id, Locat
 template <bool ALPHA, bool SRGB>
 __device__ __forceinline__ void load_shared_tables(dev::SharedTables &st)
 {
-    const dev::TableImage &src = ALPHA ? c_tables_q6 : c_tables_q12;
-    for (int i = threadIdx.x; i < 5 * dev::kFieldStride; i += blockDim.x) st.field[i] = src.field[i];
-    for (int i = threadIdx.x; i < 244; i += blockDim.x) st.trit_scattered[i] = src.trit_scattered[i];
-    if (SRGB) for (int i = threadIdx.x; i < 256; i += blockDim.x) st.lut_rgb[i] = c_srgb_lut[i];
+    static_assert(sizeof(dev::TableImage) % 16 == 0 && offsetof(dev::SharedTables, lut_rgb) == sizeof(dev::TableImage), "table layout");
+    const uint4 *src = reinterpret_cast<const uint4 *>(ALPHA ? &g_tables_q6 : &g_tables_q12);
+    uint4 *dst = reinterpret_cast<uint4 *>(&st);
+    for (int i = threadIdx.x; i < int(sizeof(dev::TableImage) / 16); i += blockDim.x) dst[i] = __ldg(src + i);
+    if (SRGB) {
+        const uint4 *lsrc = reinterpret_cast<const uint4 *>(&g_srgb_lut);
+        uint4 *ldst = reinterpret_cast<uint4 *>(st.lut_rgb);
+        for (int i = threadIdx.x; i < 64; i += blockDim.x) ldst[i] = __ldg(lsrc + i);
+    }
 }
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return uint32_t(__cvta_generic_to_shared(p)); }
@@ -335,7 +355,14 @@ constexpr size_t kSmem4x4S = size_t(16) * kThreads4x4S * sizeof(float4) + sizeof
 // 6x6: 36 texels do not fit registers as floats; each thread parks its block
 // as float4[36] in its own shared-memory column (conflict-free: bank = lane).
 // ---------------------------------------------------------------------------
-constexpr int kThreads6x6 = 128;
+#ifndef ASTC_THREADS_6X6
+#define ASTC_THREADS_6X6 128
+#endif
+#ifndef ASTC_BPT_6X6
+#define ASTC_BPT_6X6 4
+#endif
+constexpr int kThreads6x6 = ASTC_THREADS_6X6;
+constexpr int kBlocksPerThread6x6 = ASTC_BPT_6X6;
 
 struct Texels6x6 {
     const float4 *col;                                    // &smem[threadIdx.x], stride kThreads6x6
@@ -356,42 +383,46 @@ encode6x6_kernel(const EncodeParams p)
     dev::SharedTables &st = *reinterpret_cast<dev::SharedTables *>(s_tex + 36 * kThreads6x6);
     load_shared_tables<ALPHA, SRGB>(st);
     __syncthreads();
-
-    const uint64_t id = uint64_t(blockIdx.x) * kThreads6x6 + threadIdx.x;
-    Located loc;
-    if (!locate<BATCH>(p, id, loc)) return;
-
+    const uint32_t s_field = smem_addr(st.field), s_trit = smem_addr(st.trit_scattered);
     float4 *col = s_tex + threadIdx.x;
-    f2 sum_lo = dev::bc(0.f), sum_hi = dev::bc(0.f);
-    const int x0 = loc.bx * 6, y0 = loc.by * 6;
-    const uint8_t *base = loc.rgba + size_t(y0) * loc.pitch + size_t(x0) * 4u;
-    auto park = [&](int k, uint32_t w) {
-        const Texel t = convert_texel<SRGB, NORMAL>(w, st.lut_rgb, sum_lo, sum_hi);
-        col[k * kThreads6x6] = make_float4(t.lo.x, t.lo.y, t.hi.x, t.hi.y);
-    };
-    if ((loc.flags & kFlagAligned8) && x0 + 6 <= loc.width && y0 + 6 <= loc.height) {
-        // interior: a block row is 24 B = three 8-byte loads; a warp covers 768
-        // contiguous bytes per texel row.
+
+    // CTA b owns ids [b*BPT*T, (b+1)*BPT*T); a thread re-uses its own shared-memory column for
+    // each of its blocks (only it reads or writes that column: no barrier between passes).
+    uint64_t id = uint64_t(blockIdx.x) * (kBlocksPerThread6x6 * kThreads6x6) + threadIdx.x;
+#pragma unroll 1
+    for (int pass = 0; pass < kBlocksPerThread6x6; ++pass, id += kThreads6x6) {
+        Located loc;
+        if (!locate<BATCH>(p, id, loc)) return;
+        f2 sum_lo = dev::bc(0.f), sum_hi = dev::bc(0.f);
+        const int x0 = loc.bx * 6, y0 = loc.by * 6;
+        const uint8_t *base = loc.rgba + size_t(y0) * loc.pitch + size_t(x0) * 4u;
+        auto park = [&](int k, uint32_t w) {
+            const Texel t = convert_texel<SRGB, NORMAL>(w, st.lut_rgb, sum_lo, sum_hi);
+            col[k * kThreads6x6] = make_float4(t.lo.x, t.lo.y, t.hi.x, t.hi.y);
+        };
+        if ((loc.flags & kFlagAligned8) && x0 + 6 <= loc.width && y0 + 6 <= loc.height) {
+            // interior: a block row is 24 B = three 8-byte loads; a warp covers 768
+            // contiguous bytes per texel row.  All 18 loads are issued before the first use.
+            uint2 rows[18];
 #pragma unroll
-        for (int r = 0; r < 6; ++r) {
-            const uint2 *src = (const uint2 *)(base + size_t(r) * loc.pitch);
-            const uint2 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
-            park(6 * r + 0, a.x); park(6 * r + 1, a.y);
-            park(6 * r + 2, b.x); park(6 * r + 3, b.y);
-            park(6 * r + 4, c.x); park(6 * r + 5, c.y);
-        }
-    } else {
+            for (int r = 0; r < 6; ++r) {
+                const uint2 *src = (const uint2 *)(base + size_t(r) * loc.pitch);
+                rows[3 * r + 0] = __ldg(src); rows[3 * r + 1] = __ldg(src + 1); rows[3 * r + 2] = __ldg(src + 2);
+            }
+#pragma unroll
+            for (int i = 0; i < 18; ++i) { park(2 * i, rows[i].x); park(2 * i + 1, rows[i].y); }
+        } else {
 #pragma unroll 6
-        for (int k = 0; k < 36; ++k) {
-            const int kx = k % 6, ky = k / 6;
-            const bool inside = x0 + kx < loc.width && y0 + ky < loc.height;
-            park(k, inside ? __ldg((const uint32_t *)(base + size_t(ky) * loc.pitch + size_t(kx) * 4u)) : 0u);
+            for (int k = 0; k < 36; ++k) {
+                const int kx = k % 6, ky = k / 6;
+                const bool inside = x0 + kx < loc.width && y0 + ky < loc.height;
+                park(k, inside ? __ldg((const uint32_t *)(base + size_t(ky) * loc.pitch + size_t(kx) * 4u)) : 0u);
+            }
         }
+        if (NORMAL) sum_hi = dev::bc(36.0f * 255.0f);
+        Texels6x6 tx{col};
+        *loc.out = dev::encode_block<6, ALPHA, NORMAL>(tx, sum_lo, sum_hi, s_field, s_trit);
     }
-    if (NORMAL) sum_hi = dev::bc(36.0f * 255.0f);
-    // each thread reads back only its own column: no barrier needed
-    Texels6x6 tx{col};
-    *loc.out = dev::encode_block<6, ALPHA, NORMAL>(tx, sum_lo, sum_hi, smem_addr(st.field), smem_addr(st.trit_scattered));
 }
 
 constexpr size_t kSmem6x6 = size_t(36) * kThreads6x6 * sizeof(float4) + sizeof(dev::SharedTables);
@@ -418,7 +449,8 @@ static cudaError_t launch_variant(int dim, const EncodeParams &p, cudaStream_t s
         encode4x4_kernel<ALPHA, NORMAL, SRGB, BATCH><<<unsigned(ctas), kThreads4x4, 0, stream>>>(p);
 #endif
     } else {
-        const uint64_t ctas = (p.total_blocks + kThreads6x6 - 1) / kThreads6x6;
+        constexpr uint64_t per_cta6 = uint64_t(kThreads6x6) * kBlocksPerThread6x6;
+        const uint64_t ctas = (p.total_blocks + per_cta6 - 1) / per_cta6;
         if (ctas > 0x7FFFFFFFull) return cudaErrorInvalidConfiguration;
         auto kern = encode6x6_kernel<ALPHA, NORMAL, SRGB, BATCH>;
         static thread_local int configured_device = -1;

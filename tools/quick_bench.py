@@ -26,6 +26,8 @@ if __name__ == "__main__":
         run(16384, 16384, A.encode_option(), "4x4 rgb")
         run(4096, 4096, A.encode_option(has_alpha=True), "4x4 rgba")
         run(8192, 8192, A.encode_option(is6x6=True, has_alpha=True, srgb=True), "6x6 rgba srgb")
+        run(8192, 8192, A.encode_option(is6x6=True), "6x6 rgb")
+        run(4096, 4096, A.encode_option(srgb=True), "4x4 rgb srgb")
         sys.exit(0)
     print(A.version(), torch.cuda.get_device_name(0))
     run(4096, 4096, A.encode_option(), "4x4 rgb")
