@@ -223,35 +223,33 @@ encode4x4_kernel(const EncodeParams p)
 
     // CTA b owns ids [b*BPT*T, (b+1)*BPT*T); pass i takes the i-th run of T consecutive ids, so a
     // warp still reads 512 contiguous bytes per texel row and stores 512 contiguous bytes.
+    // Little state survives an encode: the prefetched rows, the id, and the output pointer.
     uint64_t id = uint64_t(blockIdx.x) * (kBlocksPerThread4x4 * kThreads4x4) + threadIdx.x;
-    Located loc;
     Rows4x4 rows;
-    bool valid = locate<BATCH>(p, id, loc);
-    if (valid) fetch_rows(loc, rows);
+    uint4 *out;
+    {
+        Located loc;
+        if (!locate<BATCH>(p, id, loc)) return;
+        fetch_rows(loc, rows);
+        out = loc.out;
+    }
 #pragma unroll 1
-    for (int pass = 0; pass < kBlocksPerThread4x4 && valid; ++pass) {
-        const Located cur = loc;
-        const Rows4x4 now = rows;
-#if ASTC_PREFETCH_4X4
-        if (pass + 1 < kBlocksPerThread4x4) {              // software prefetch: next block's rows in flight during this encode
-            id += kThreads4x4;
-            valid = locate<BATCH>(p, id, loc);
-            if (valid) fetch_rows(loc, rows);
-        }
-#endif
+    for (int pass = 0;; ++pass) {
         Texels4x4 tx;
         f2 sum_lo = dev::bc(0.f), sum_hi = dev::bc(0.f);
-        if (now.fast) {
+        if (rows.fast) {
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
-                tx.t[4 * r + 0] = convert_texel<SRGB, NORMAL>(now.r[r].x, st.lut_rgb, sum_lo, sum_hi);
-                tx.t[4 * r + 1] = convert_texel<SRGB, NORMAL>(now.r[r].y, st.lut_rgb, sum_lo, sum_hi);
-                tx.t[4 * r + 2] = convert_texel<SRGB, NORMAL>(now.r[r].z, st.lut_rgb, sum_lo, sum_hi);
-                tx.t[4 * r + 3] = convert_texel<SRGB, NORMAL>(now.r[r].w, st.lut_rgb, sum_lo, sum_hi);
+                tx.t[4 * r + 0] = convert_texel<SRGB, NORMAL>(rows.r[r].x, st.lut_rgb, sum_lo, sum_hi);
+                tx.t[4 * r + 1] = convert_texel<SRGB, NORMAL>(rows.r[r].y, st.lut_rgb, sum_lo, sum_hi);
+                tx.t[4 * r + 2] = convert_texel<SRGB, NORMAL>(rows.r[r].z, st.lut_rgb, sum_lo, sum_hi);
+                tx.t[4 * r + 3] = convert_texel<SRGB, NORMAL>(rows.r[r].w, st.lut_rgb, sum_lo, sum_hi);
             }
         } else {
             // edge / unaligned: per-texel loads, out-of-range texels read as 0
             // like Texture2D.Load (ASTC_Encode.hlsl:574); the UNORM / sRGB value of byte 0 is 0.
+            Located cur;
+            locate<BATCH>(p, id, cur);
             const int x0 = cur.bx * 4, y0 = cur.by * 4;
             const uint8_t *base = cur.rgba + size_t(y0) * cur.pitch + size_t(x0) * 4u;
 #pragma unroll
@@ -262,15 +260,21 @@ encode4x4_kernel(const EncodeParams p)
                 tx.t[k] = convert_texel<SRGB, NORMAL>(w, st.lut_rgb, sum_lo, sum_hi);
             }
         }
-        // one coalesced 16-byte store per thread
-        *cur.out = dev::encode_block<4, ALPHA, NORMAL>(tx, sum_lo, sum_hi, s_field, s_trit);
-#if !ASTC_PREFETCH_4X4
-        if (pass + 1 < kBlocksPerThread4x4) {
+        // software prefetch: the next block's rows are in flight during this block's arithmetic
+        uint4 *const out_cur = out;
+        bool more = pass + 1 < kBlocksPerThread4x4;
+        if (more) {
             id += kThreads4x4;
-            valid = locate<BATCH>(p, id, loc);
-            if (valid) fetch_rows(loc, rows);
+            Located nxt;
+            more = locate<BATCH>(p, id, nxt);
+            if (more) {
+                fetch_rows(nxt, rows);
+                out = nxt.out;
+            }
         }
-#endif
+        // one coalesced 16-byte store per thread
+        *out_cur = dev::encode_block<4, ALPHA, NORMAL>(tx, sum_lo, sum_hi, s_field, s_trit);
+        if (!more) break;
     }
 }
 
