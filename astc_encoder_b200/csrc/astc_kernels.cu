@@ -212,6 +212,94 @@ __device__ __forceinline__ void fetch_rows(const Located &loc, Rows4x4 &rows)
     }
 }
 
+#ifndef ASTC_CPASYNC_4X4
+#define ASTC_CPASYNC_4X4 0
+#endif
+
+#if ASTC_CPASYNC_4X4
+// Prefetch of the next block's four 16-byte texel rows with cp.async (LDGSTS) into a
+// per-thread slot of shared memory: the copy is in flight during the current block's
+// arithmetic and holds no registers.  Each thread reads back only what it copied itself,
+// so cp.async.wait_group is the only synchronisation.
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void *g)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ bool prefetch_rows(const Located &loc, uint32_t slot)
+{
+    const int x0 = loc.bx * 4, y0 = loc.by * 4;
+    const bool fast = (loc.flags & kFlagAligned16) && x0 + 4 <= loc.width && y0 + 4 <= loc.height;
+    if (fast) {
+        const uint8_t *base = loc.rgba + size_t(y0) * loc.pitch + size_t(x0) * 4u;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) cp_async16(slot + uint32_t(r) * (kThreads4x4 * 16u), base + size_t(r) * loc.pitch);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    return fast;
+}
+
+template <bool ALPHA, bool NORMAL, bool SRGB, bool BATCH>
+__global__ void __launch_bounds__(kThreads4x4, ASTC_MINBLOCKS_4X4)
+encode4x4_kernel(const EncodeParams p)
+{
+    __shared__ dev::SharedTables st;
+    __shared__ uint4 s_rows[2][4][kThreads4x4];
+    load_shared_tables<ALPHA, SRGB>(st);
+    __syncthreads();
+    const uint32_t s_field = smem_addr(st.field), s_trit = smem_addr(st.trit_scattered);
+
+    uint64_t id = uint64_t(blockIdx.x) * (kBlocksPerThread4x4 * kThreads4x4) + threadIdx.x;
+    uint4 *out;
+    bool fast;
+    {
+        Located loc;
+        if (!locate<BATCH>(p, id, loc)) return;
+        fast = prefetch_rows(loc, smem_addr(&s_rows[0][0][threadIdx.x]));
+        out = loc.out;
+    }
+#pragma unroll 1
+    for (int pass = 0;; ++pass) {
+        Texels4x4 tx;
+        f2 sum_lo = dev::bc(0.f), sum_hi = dev::bc(0.f);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (fast) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const uint4 row = s_rows[pass & 1][r][threadIdx.x];
+                tx.t[4 * r + 0] = convert_texel<SRGB, NORMAL>(row.x, st.lut_rgb, sum_lo, sum_hi);
+                tx.t[4 * r + 1] = convert_texel<SRGB, NORMAL>(row.y, st.lut_rgb, sum_lo, sum_hi);
+                tx.t[4 * r + 2] = convert_texel<SRGB, NORMAL>(row.z, st.lut_rgb, sum_lo, sum_hi);
+                tx.t[4 * r + 3] = convert_texel<SRGB, NORMAL>(row.w, st.lut_rgb, sum_lo, sum_hi);
+            }
+        } else {
+            Located cur;
+            locate<BATCH>(p, id, cur);
+            const int x0 = cur.bx * 4, y0 = cur.by * 4;
+            const uint8_t *base = cur.rgba + size_t(y0) * cur.pitch + size_t(x0) * 4u;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const int x = x0 + (k & 3), y = y0 + (k >> 2);
+                const bool inside = x < cur.width && y < cur.height;
+                const uint32_t w = inside ? __ldg((const uint32_t *)(base + size_t(k >> 2) * cur.pitch + size_t(k & 3) * 4u)) : 0u;
+                tx.t[k] = convert_texel<SRGB, NORMAL>(w, st.lut_rgb, sum_lo, sum_hi);
+            }
+        }
+        uint4 *const out_cur = out;
+        bool more = pass + 1 < kBlocksPerThread4x4;
+        if (more) {
+            id += kThreads4x4;
+            Located nxt;
+            more = locate<BATCH>(p, id, nxt);
+            if (more) {
+                fast = prefetch_rows(nxt, smem_addr(&s_rows[(pass + 1) & 1][0][threadIdx.x]));
+                out = nxt.out;
+            }
+        }
+        *out_cur = dev::encode_block<4, ALPHA, NORMAL>(tx, sum_lo, sum_hi, s_field, s_trit);
+        if (!more) break;
+    }
+}
+#else
 template <bool ALPHA, bool NORMAL, bool SRGB, bool BATCH>
 __global__ void __launch_bounds__(kThreads4x4, ASTC_MINBLOCKS_4X4)
 encode4x4_kernel(const EncodeParams p)
@@ -277,6 +365,8 @@ encode4x4_kernel(const EncodeParams p)
         if (!more) break;
     }
 }
+
+#endif  // ASTC_CPASYNC_4X4
 
 #if ASTC_4X4_SMEM
 // ---------------------------------------------------------------------------

@@ -19,7 +19,8 @@ def run(w, h, opt, label, iters=10):
     torch.cuda.synchronize()
     ts = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(iters))
     med = ts[len(ts) // 2]
-    print(f"{label}: {w}x{h} median {med:.3f} ms best {ts[0]:.3f} ms -> {w*h/med/1e6:.1f} Gtexel/s", flush=True)
+    chk = int(out.view(torch.int64).sum().item()) & 0xFFFFFFFFFFFF   # compare across experiment builds
+    print(f"{label}: {w}x{h} median {med:.3f} ms best {ts[0]:.3f} ms -> {w*h/med/1e6:.1f} Gtexel/s  chk {chk:012x}", flush=True)
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "short":
