@@ -14,7 +14,6 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -74,70 +73,6 @@ astc::ImageDesc make_desc(const uint8_t *rgba, uint8_t *blocks, size_t pitch, in
     d.flags = align_flags(rgba, pitch);
     return d;
 }
-
-// ---------------------------------------------------------------------------
-// Texture objects over caller memory.  The reference reads its source through an SRV
-// (astc_encode.h:107-120) and lets the texture unit turn UNORM8 into float; the linear 4x4
-// kernels here do the same.  A texture object is a descriptor of (pointer, pitch, size):
-// it owns no memory, so objects are cached by geometry and recycled when the cache is full.
-// ---------------------------------------------------------------------------
-struct TexEntry {
-    int device;
-    const void *ptr;
-    size_t pitch;
-    int width, height;
-    cudaTextureObject_t tex;
-};
-std::mutex g_tex_mutex;
-std::vector<TexEntry> g_tex_cache;
-constexpr size_t kTexCacheCap = 256;
-
-bool tex_eligible(const void *ptr, size_t pitch, int width, int height)
-{
-    return reinterpret_cast<uintptr_t>(ptr) % astc::kTexBaseAlign == 0 && pitch % astc::kTexPitchAlign == 0 &&
-           width <= astc::kTexMaxWidth && height <= astc::kTexMaxHeight && pitch <= 2097120u;
-}
-
-// 0 when the geometry does not qualify or creation fails (callers then use the load path).
-cudaTextureObject_t texture_for(const void *ptr, size_t pitch, int width, int height)
-{
-    if (!tex_eligible(ptr, pitch, width, height)) return 0;
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-    std::lock_guard<std::mutex> lock(g_tex_mutex);
-    for (const TexEntry &e : g_tex_cache)
-        if (e.device == dev && e.ptr == ptr && e.pitch == pitch && e.width == width && e.height == height) return e.tex;
-    if (g_tex_cache.size() >= kTexCacheCap) {
-        // descriptors may still be referenced by kernels in flight: drain before recycling
-        cudaDeviceSynchronize();
-        for (const TexEntry &e : g_tex_cache)
-            if (e.device == dev) cudaDestroyTextureObject(e.tex);
-        g_tex_cache.erase(std::remove_if(g_tex_cache.begin(), g_tex_cache.end(), [dev](const TexEntry &e) { return e.device == dev; }),
-                          g_tex_cache.end());
-    }
-    cudaResourceDesc rd{};
-    rd.resType = cudaResourceTypePitch2D;
-    rd.res.pitch2D.devPtr = const_cast<void *>(ptr);
-    rd.res.pitch2D.desc = cudaCreateChannelDesc<uchar4>();
-    rd.res.pitch2D.width = size_t(width);
-    rd.res.pitch2D.height = size_t(height);
-    rd.res.pitch2D.pitchInBytes = pitch;
-    cudaTextureDesc td{};
-    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeBorder;   // outside -> 0, like Texture2D.Load
-    td.filterMode = cudaFilterModePoint;
-    td.readMode = cudaReadModeNormalizedFloat;                   // c / 255.0f, exact (checked on the device by the tests)
-    td.normalizedCoords = 0;
-    cudaTextureObject_t tex = 0;
-    if (cudaCreateTextureObject(&tex, &rd, &td, nullptr) != cudaSuccess) {
-        cudaGetLastError();
-        return 0;
-    }
-    g_tex_cache.push_back(TexEntry{dev, ptr, pitch, width, height, tex});
-    return tex;
-}
-
-// The texture path serves linear (non -srgb) 4x4 encodes.
-bool wants_texture(const astc_b200_option *o, int dim) { return dim == 4 && (!o->srgb || o->is_normal_map); }
 
 int ensure_pool()
 {
@@ -262,8 +197,6 @@ int astc_b200_encode_device(const uint8_t *d_rgba, int width, int height, size_t
     const int d = dim_of(opt);
     astc::EncodeParams p{};
     p.single = make_desc(d_rgba, d_blocks, pitch_bytes, width, height, d, 0);
-    if (wants_texture(opt, d)) p.single.tex = texture_for(d_rgba, pitch_bytes, width, height);
-    p.all_textured = p.single.tex != 0;
     p.table = nullptr;
     p.count = 1;
     p.total_blocks = uint64_t(p.single.blocks_x) * uint64_t((height + d - 1) / d);
@@ -303,8 +236,6 @@ int astc_b200_encode_host(const uint8_t *h_rgba, int width, int height, size_t p
     if (err == cudaSuccess) err = cudaEventRecord(ready, streams[0]);
     for (int s = 1; s < kStreams && err == cudaSuccess; ++s) err = cudaStreamWaitEvent(streams[s], ready, 0);
 
-    // one texture over the whole upload; every band addresses it with its own row origin
-    const cudaTextureObject_t tex = (err == cudaSuccess && wants_texture(opt, d)) ? texture_for(d_in, d_pitch, width, height) : 0;
     for (int b = 0; b < nbands && err == cudaSuccess; ++b) {
         cudaStream_t st = streams[b % kStreams];
         const int64_t r0 = int64_t(b) * rows_per_band, r1 = std::min<int64_t>(by, r0 + rows_per_band);
@@ -315,9 +246,6 @@ int astc_b200_encode_host(const uint8_t *h_rgba, int width, int height, size_t p
         if (err != cudaSuccess) break;
         astc::EncodeParams p{};
         p.single = make_desc(d_in + size_t(y0) * d_pitch, d_out + out_off, d_pitch, width, int(y1 - y0), d, 0);
-        p.single.tex = tex;
-        p.single.tex_y0 = int32_t(y0);
-        p.all_textured = tex != 0;
         p.count = 1;
         p.total_blocks = uint64_t(bx) * uint64_t(r1 - r0);
         err = astc::launch_encode(d, opt->has_alpha != 0, opt->is_normal_map != 0, opt->srgb != 0, p, st);

@@ -115,46 +115,74 @@ __device__ __forceinline__ Texel convert_texel(uint32_t w, const float *lut_rgb,
 }
 
 // ---------------------------------------------------------------------------
-// block location
+// block walk
 // ---------------------------------------------------------------------------
-struct Located {
-    const uint8_t *rgba;
-    uint4 *out;
-    size_t pitch;
-    int width, height, bx, by;
-    uint32_t flags;
-    unsigned long long tex;
-    int tex_y0;
-};
-
-// Single image: divide the linear id.  Batch: binary search the prefix table.
+// A thread visits the block ids  first, first + stride, first + 2*stride, ...  The walk keeps
+// the block's image and its (bx, by) incrementally: one division when it starts and one each
+// time it crosses the end of a block row or of an image; the other steps are adds.  (Dividing
+// the linear id for every block, as MainCS does at ASTC_Encode.hlsl:561-562, costs ~25 issue
+// slots of a ~1100-slot block.)
 template <bool BATCH>
-__device__ __forceinline__ bool locate(const EncodeParams &p, uint64_t id, Located &loc)
-{
-    if (id >= p.total_blocks) return false;
-    ImageDesc d = p.single;
-    if (BATCH) {
-        const ImageDesc *__restrict__ table = p.table;
-        int lo = 0, hi = p.count - 1;
-        while (lo < hi) {                                  // last image with first_block <= id
-            const int mid = (lo + hi + 1) >> 1;
-            if (__ldg(&table[mid].first_block) <= id) lo = mid; else hi = mid - 1;
-        }
-        d = table[lo];
+struct Walk {
+    uint32_t local;          // block index inside the image
+    uint32_t bx, by;
+    int idx;                 // image index (batch only)
+
+    __device__ __forceinline__ const ImageDesc &desc(const EncodeParams &p) const { return BATCH ? p.table[idx] : p.single; }
+    __device__ __forceinline__ uint32_t image_blocks(const EncodeParams &p) const
+    {
+        if (!BATCH) return uint32_t(p.total_blocks);
+        const uint64_t next = idx + 1 < p.count ? __ldg(&p.table[idx + 1].first_block) : p.total_blocks;
+        return uint32_t(next - __ldg(&p.table[idx].first_block));
     }
-    const uint32_t local = uint32_t(id - d.first_block);
-    loc.by = int(local / d.blocks_x);
-    loc.bx = int(local - uint32_t(loc.by) * d.blocks_x);
-    loc.rgba = d.rgba;
-    loc.out = reinterpret_cast<uint4 *>(d.blocks) + local;
-    loc.pitch = d.pitch;
-    loc.width = d.width;
-    loc.height = d.height;
-    loc.flags = d.flags;
-    loc.tex = d.tex;
-    loc.tex_y0 = d.tex_y0;
-    return true;
-}
+    __device__ __forceinline__ void divide(uint32_t blocks_x)
+    {
+        by = local / blocks_x;
+        bx = local - by * blocks_x;
+    }
+    __device__ __forceinline__ bool start(const EncodeParams &p, uint64_t id)
+    {
+        if (id >= p.total_blocks) return false;
+        idx = 0;
+        uint64_t first = 0;
+        if (BATCH) {
+            const ImageDesc *__restrict__ table = p.table;
+            int lo = 0, hi = p.count - 1;
+            while (lo < hi) {                              // last image with first_block <= id
+                const int mid = (lo + hi + 1) >> 1;
+                if (__ldg(&table[mid].first_block) <= id) lo = mid; else hi = mid - 1;
+            }
+            idx = lo;
+            first = __ldg(&table[lo].first_block);
+        }
+        local = uint32_t(id - first);
+        divide(BATCH ? __ldg(&p.table[idx].blocks_x) : p.single.blocks_x);
+        return true;
+    }
+    __device__ __forceinline__ bool advance(const EncodeParams &p, uint32_t stride)
+    {
+        local += stride;
+        bx += stride;
+        uint32_t n = image_blocks(p);
+        if (local >= n) {
+            if (!BATCH) return false;
+            do {
+                local -= n;
+                if (++idx >= p.count) return false;
+                n = image_blocks(p);
+            } while (local >= n);
+            divide(__ldg(&p.table[idx].blocks_x));
+        } else {
+            const uint32_t blocks_x = BATCH ? __ldg(&p.table[idx].blocks_x) : p.single.blocks_x;
+            if (bx >= blocks_x) divide(blocks_x);
+        }
+        return true;
+    }
+    __device__ __forceinline__ uint4 *out(const EncodeParams &p) const
+    {
+        return reinterpret_cast<uint4 *>(BATCH ? p.table[idx].blocks : p.single.blocks) + local;
+    }
+};
 
 template <bool ALPHA, bool SRGB>
 __device__ __forceinline__ void load_shared_tables(dev::SharedTables &st)
@@ -187,56 +215,34 @@ struct Texels4x4 {
 #ifndef ASTC_MINBLOCKS_4X4
 #define ASTC_MINBLOCKS_4X4 3
 #endif
-constexpr int kThreads4x4 = ASTC_THREADS_4X4;
-
-#ifndef ASTC_PREFETCH_4X4
-#define ASTC_PREFETCH_4X4 1
-#endif
 #ifndef ASTC_BPT_4X4
 #define ASTC_BPT_4X4 8
 #endif
+constexpr int kThreads4x4 = ASTC_THREADS_4X4;
 constexpr int kBlocksPerThread4x4 = ASTC_BPT_4X4;   // ASTC blocks each thread encodes, one after the other
 
-// The four 16-byte texel rows of an interior block, fetched one block ahead of use.
-struct Rows4x4 {
-    uint4 r[4];
-    bool fast;
-};
-
-__device__ __forceinline__ void fetch_rows(const Located &loc, Rows4x4 &rows)
-{
-    const int x0 = loc.bx * 4, y0 = loc.by * 4;
-    rows.fast = (loc.flags & kFlagAligned16) && x0 + 4 <= loc.width && y0 + 4 <= loc.height;
-    if (rows.fast) {
-        // one 16-byte read-only load per texel row; adjacent threads read adjacent
-        // 16 B, i.e. 512 contiguous bytes per warp per row.
-        const uint8_t *base = loc.rgba + size_t(y0) * loc.pitch + size_t(x0) * 4u;
-#pragma unroll
-        for (int r = 0; r < 4; ++r) rows.r[r] = __ldg((const uint4 *)(base + size_t(r) * loc.pitch));
-    }
-}
-
-#ifndef ASTC_CPASYNC_4X4
-#define ASTC_CPASYNC_4X4 0
-#endif
-
-#if ASTC_CPASYNC_4X4
-// Prefetch of the next block's four 16-byte texel rows with cp.async (LDGSTS) into a
-// per-thread slot of shared memory: the copy is in flight during the current block's
-// arithmetic and holds no registers.  Each thread reads back only what it copied itself,
-// so cp.async.wait_group is the only synchronisation.
+// The four 16-byte texel rows of the thread's next block travel global -> shared memory by
+// cp.async (LDGSTS) while the current block is being encoded: the copy holds no registers
+// (a register prefetch costs 16 and pushed the kernel into spills) and needs no barrier, since a
+// thread reads back only the slots it filled itself -- cp.async.wait_group is the whole handshake.
 __device__ __forceinline__ void cp_async16(uint32_t saddr, const void *g)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
 }
-__device__ __forceinline__ bool prefetch_rows(const Located &loc, uint32_t slot)
+
+// Returns whether the block took the vector path (whole block inside the image, 16-byte aligned rows).
+template <bool BATCH>
+__device__ __forceinline__ bool prefetch_rows4x4(const EncodeParams &p, const Walk<BATCH> &wk, uint32_t slot)
 {
-    const int x0 = loc.bx * 4, y0 = loc.by * 4;
-    const bool fast = (loc.flags & kFlagAligned16) && x0 + 4 <= loc.width && y0 + 4 <= loc.height;
+    const ImageDesc &d = wk.desc(p);
+    const uint32_t x0 = wk.bx * 4u, y0 = wk.by * 4u;
+    const bool fast = (d.flags & kFlagAligned16) && x0 + 4u <= uint32_t(d.width) && y0 + 4u <= uint32_t(d.height);
     if (fast) {
-        const uint8_t *base = loc.rgba + size_t(y0) * loc.pitch + size_t(x0) * 4u;
+        // adjacent threads copy adjacent 16 B: 512 contiguous bytes per warp per texel row
+        const size_t pitch = d.pitch;
+        const uint8_t *src = d.rgba + size_t(y0) * pitch + size_t(x0) * 4u;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) cp_async16(slot + uint32_t(r) * (kThreads4x4 * 16u), base + size_t(r) * loc.pitch);
+        for (int r = 0; r < 4; ++r, src += pitch) cp_async16(slot + uint32_t(r) * (kThreads4x4 * 16u), src);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     return fast;
@@ -247,20 +253,18 @@ __global__ void __launch_bounds__(kThreads4x4, ASTC_MINBLOCKS_4X4)
 encode4x4_kernel(const EncodeParams p)
 {
     __shared__ dev::SharedTables st;
-    __shared__ uint4 s_rows[2][4][kThreads4x4];
+    __shared__ uint4 s_rows[2][4][kThreads4x4];                 // cp.async landing slots, double-buffered
     load_shared_tables<ALPHA, SRGB>(st);
     __syncthreads();
     const uint32_t s_field = smem_addr(st.field), s_trit = smem_addr(st.trit_scattered);
+    const uint32_t slot0 = smem_addr(&s_rows[0][0][threadIdx.x]);
+    constexpr uint32_t kSlotStride = 4u * kThreads4x4 * 16u;
 
-    uint64_t id = uint64_t(blockIdx.x) * (kBlocksPerThread4x4 * kThreads4x4) + threadIdx.x;
-    uint4 *out;
-    bool fast;
-    {
-        Located loc;
-        if (!locate<BATCH>(p, id, loc)) return;
-        fast = prefetch_rows(loc, smem_addr(&s_rows[0][0][threadIdx.x]));
-        out = loc.out;
-    }
+    // CTA b owns ids [b*BPT*T, (b+1)*BPT*T); pass i takes the i-th run of T consecutive ids, so a
+    // warp reads 512 contiguous bytes per texel row and stores 512 contiguous bytes.
+    Walk<BATCH> wk;
+    if (!wk.start(p, uint64_t(blockIdx.x) * (kBlocksPerThread4x4 * kThreads4x4) + threadIdx.x)) return;
+    bool fast = prefetch_rows4x4<BATCH>(p, wk, slot0);
 #pragma unroll 1
     for (int pass = 0;; ++pass) {
         Texels4x4 tx;
@@ -276,434 +280,28 @@ encode4x4_kernel(const EncodeParams p)
                 tx.t[4 * r + 3] = convert_texel<SRGB, NORMAL>(row.w, st.lut_rgb, sum_lo, sum_hi);
             }
         } else {
-            Located cur;
-            locate<BATCH>(p, id, cur);
-            const int x0 = cur.bx * 4, y0 = cur.by * 4;
-            const uint8_t *base = cur.rgba + size_t(y0) * cur.pitch + size_t(x0) * 4u;
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const int x = x0 + (k & 3), y = y0 + (k >> 2);
-                const bool inside = x < cur.width && y < cur.height;
-                const uint32_t w = inside ? __ldg((const uint32_t *)(base + size_t(k >> 2) * cur.pitch + size_t(k & 3) * 4u)) : 0u;
-                tx.t[k] = convert_texel<SRGB, NORMAL>(w, st.lut_rgb, sum_lo, sum_hi);
-            }
-        }
-        uint4 *const out_cur = out;
-        bool more = pass + 1 < kBlocksPerThread4x4;
-        if (more) {
-            id += kThreads4x4;
-            Located nxt;
-            more = locate<BATCH>(p, id, nxt);
-            if (more) {
-                fast = prefetch_rows(nxt, smem_addr(&s_rows[(pass + 1) & 1][0][threadIdx.x]));
-                out = nxt.out;
-            }
-        }
-        *out_cur = dev::encode_block<4, ALPHA, NORMAL>(tx, sum_lo, sum_hi, s_field, s_trit);
-        if (!more) break;
-    }
-}
-#else
-template <bool ALPHA, bool NORMAL, bool SRGB, bool BATCH>
-__global__ void __launch_bounds__(kThreads4x4, ASTC_MINBLOCKS_4X4)
-encode4x4_kernel(const EncodeParams p)
-{
-    __shared__ dev::SharedTables st;
-    load_shared_tables<ALPHA, SRGB>(st);
-    __syncthreads();
-    const uint32_t s_field = smem_addr(st.field), s_trit = smem_addr(st.trit_scattered);
-
-    // CTA b owns ids [b*BPT*T, (b+1)*BPT*T); pass i takes the i-th run of T consecutive ids, so a
-    // warp still reads 512 contiguous bytes per texel row and stores 512 contiguous bytes.
-    // Little state survives an encode: the prefetched rows, the id, and the output pointer.
-    uint64_t id = uint64_t(blockIdx.x) * (kBlocksPerThread4x4 * kThreads4x4) + threadIdx.x;
-    Rows4x4 rows;
-    uint4 *out;
-    {
-        Located loc;
-        if (!locate<BATCH>(p, id, loc)) return;
-        fetch_rows(loc, rows);
-        out = loc.out;
-    }
-#pragma unroll 1
-    for (int pass = 0;; ++pass) {
-        Texels4x4 tx;
-        f2 sum_lo = dev::bc(0.f), sum_hi = dev::bc(0.f);
-        if (rows.fast) {
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                tx.t[4 * r + 0] = convert_texel<SRGB, NORMAL>(rows.r[r].x, st.lut_rgb, sum_lo, sum_hi);
-                tx.t[4 * r + 1] = convert_texel<SRGB, NORMAL>(rows.r[r].y, st.lut_rgb, sum_lo, sum_hi);
-                tx.t[4 * r + 2] = convert_texel<SRGB, NORMAL>(rows.r[r].z, st.lut_rgb, sum_lo, sum_hi);
-                tx.t[4 * r + 3] = convert_texel<SRGB, NORMAL>(rows.r[r].w, st.lut_rgb, sum_lo, sum_hi);
-            }
-        } else {
             // edge / unaligned: per-texel loads, out-of-range texels read as 0
             // like Texture2D.Load (ASTC_Encode.hlsl:574); the UNORM / sRGB value of byte 0 is 0.
-            Located cur;
-            locate<BATCH>(p, id, cur);
-            const int x0 = cur.bx * 4, y0 = cur.by * 4;
-            const uint8_t *base = cur.rgba + size_t(y0) * cur.pitch + size_t(x0) * 4u;
+            const ImageDesc &d = wk.desc(p);
+            const uint32_t x0 = wk.bx * 4u, y0 = wk.by * 4u;
+            const size_t pitch = d.pitch;
+            const uint32_t width = uint32_t(d.width), height = uint32_t(d.height);
+            const uint8_t *base = d.rgba + size_t(y0) * pitch + size_t(x0) * 4u;
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
-                const int x = x0 + (k & 3), y = y0 + (k >> 2);
-                const bool inside = x < cur.width && y < cur.height;
-                const uint32_t w = inside ? __ldg((const uint32_t *)(base + size_t(k >> 2) * cur.pitch + size_t(k & 3) * 4u)) : 0u;
+                const bool inside = x0 + (k & 3) < width && y0 + (k >> 2) < height;
+                const uint32_t w = inside ? __ldg((const uint32_t *)(base + size_t(k >> 2) * pitch + size_t(k & 3) * 4u)) : 0u;
                 tx.t[k] = convert_texel<SRGB, NORMAL>(w, st.lut_rgb, sum_lo, sum_hi);
             }
         }
-        // software prefetch: the next block's rows are in flight during this block's arithmetic
-        uint4 *const out_cur = out;
-        bool more = pass + 1 < kBlocksPerThread4x4;
-        if (more) {
-            id += kThreads4x4;
-            Located nxt;
-            more = locate<BATCH>(p, id, nxt);
-            if (more) {
-                fetch_rows(nxt, rows);
-                out = nxt.out;
-            }
-        }
+        uint4 *const out = wk.out(p);
+        const bool more = pass + 1 < kBlocksPerThread4x4 && wk.advance(p, kThreads4x4);
+        if (more) fast = prefetch_rows4x4<BATCH>(p, wk, slot0 + uint32_t((pass + 1) & 1) * kSlotStride);
         // one coalesced 16-byte store per thread
-        *out_cur = dev::encode_block<4, ALPHA, NORMAL>(tx, sum_lo, sum_hi, s_field, s_trit);
+        *out = dev::encode_block<4, ALPHA, NORMAL>(tx, sum_lo, sum_hi, s_field, s_trit);
         if (!more) break;
     }
 }
-
-#endif  // ASTC_CPASYNC_4X4
-
-#ifndef ASTC_TEX_4X4
-#define ASTC_TEX_4X4 0
-#endif
-#if ASTC_TEX_4X4
-// ---------------------------------------------------------------------------
-// 4x4, linear (no -srgb): texels come through the texture unit.  A point-sampled
-// RGBA8 texture in normalized-float read mode returns exactly RN(c / 255.0f) for every
-// byte (tools/microbench/texunorm.cu checks all 256 on the device; so does the test
-// suite), which is the UNORM conversion the reference gets from its SRV -- so the
-// 16 fetches replace the load, byte unpack and divide (~200 issue slots per block).
-// Border addressing returns 0 outside the image like Texture2D.Load (ASTC_Encode.hlsl:574),
-// so edge blocks take the same path.  The fetch for the next block is issued as soon
-// as the current block's texels have been read for the last time (project_block) and
-// lands during weight quantisation and packing.
-// ---------------------------------------------------------------------------
-template <bool NORMAL>
-__device__ __forceinline__ Texel tex_fetch(unsigned long long tex, int x, int y)
-{
-    Texel t;
-    asm volatile("tex.2d.v4.f32.s32 {%0, %1, %2, %3}, [%4, {%5, %6}];"
-                 : "=f"(t.lo.x), "=f"(t.lo.y), "=f"(t.hi.x), "=f"(t.hi.y)
-                 : "l"(tex), "r"(x), "r"(y));
-    if (NORMAL) t.hi = dev::bc(1.0f);                           // :575-578, also for texels outside the image (the b, a
-                                                                // outputs are dead: ptxas drops them from the write mask)
-    return t;
-}
-
-template <bool NORMAL>
-__device__ __forceinline__ void tex_fetch_block(const Located &loc, Texels4x4 &tx)
-{
-    const int x0 = loc.bx * 4, y0 = loc.by * 4 + loc.tex_y0;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) tx.t[k] = tex_fetch<NORMAL>(loc.tex, x0 + (k & 3), y0 + (k >> 2));
-}
-
-template <bool ALPHA, bool NORMAL, bool BATCH>
-__global__ void __launch_bounds__(kThreads4x4, ASTC_MINBLOCKS_4X4)
-encode4x4_tex_kernel(const EncodeParams p)
-{
-    __shared__ dev::SharedTables st;
-    load_shared_tables<ALPHA, false>(st);
-    __syncthreads();
-    const uint32_t s_field = smem_addr(st.field), s_trit = smem_addr(st.trit_scattered);
-
-    uint64_t id = uint64_t(blockIdx.x) * (kBlocksPerThread4x4 * kThreads4x4) + threadIdx.x;
-    Texels4x4 tx;
-    uint4 *out;
-    {
-        Located loc;
-        if (!locate<BATCH>(p, id, loc)) return;
-        tex_fetch_block<NORMAL>(loc, tx);
-        out = loc.out;
-    }
-#pragma unroll 1
-    for (int pass = 0;; ++pass) {
-        // sum of texel * 255 (ASTC_Encode.hlsl:142-147): RN(raw * 255) == c for every byte, and the
-        // running sum of bytes stays an exact integer below 2^12, so fma(raw, 255, sum) == sum + c.
-        f2 sum_lo = dev::bc(0.f), sum_hi = dev::bc(0.f);
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            sum_lo = dev::fma2(tx.t[k].lo, dev::bc(255.0f), sum_lo);
-            if (!NORMAL) sum_hi = dev::fma2(tx.t[k].hi, dev::bc(255.0f), sum_hi);
-        }
-        const dev::BlockStats bs = dev::block_stats<4, NORMAL>(tx, sum_lo, sum_hi);
-        f2 axis_lo, axis_hi;
-        dev::power_iteration<NORMAL>(bs.m, axis_lo, axis_hi);
-        const dev::Projected pr = dev::project_block<4, ALPHA, NORMAL>(tx, bs.mean_lo, bs.mean_hi, axis_lo, axis_hi);
-        // the texel registers are free: the next block's fetches go out now
-        uint4 *const out_cur = out;
-        bool more = pass + 1 < kBlocksPerThread4x4;
-        if (more) {
-            id += kThreads4x4;
-            Located nxt;
-            more = locate<BATCH>(p, id, nxt);
-            if (more) {
-                tex_fetch_block<NORMAL>(nxt, tx);
-                out = nxt.out;
-            }
-        }
-        *out_cur = dev::pack_block<ALPHA>(pr, s_field, s_trit);
-        if (!more) break;
-    }
-}
-#endif  // ASTC_TEX_4X4
-
-#ifndef ASTC_PAIR_4X4
-#define ASTC_PAIR_4X4 0
-#endif
-#if ASTC_PAIR_4X4
-// ---------------------------------------------------------------------------
-// 4x4, two blocks per thread in flight.  The principal-axis power iteration is a serial
-// chain that leaves the issue slots of a 3-warp sub-partition half empty; running it for
-// two independent blocks in lock step (power_iteration_pair) fills them.  Block A's texels
-// wait in shared memory (one float4 column per thread, conflict-free) while block B's stay
-// in registers; the next pair's texel rows arrive by cp.async (LDGSTS) meanwhile and hold no
-// registers.
-// ---------------------------------------------------------------------------
-#ifndef ASTC_THREADS_PAIR
-#define ASTC_THREADS_PAIR 128
-#endif
-#ifndef ASTC_MINBLOCKS_PAIR
-#define ASTC_MINBLOCKS_PAIR 3
-#endif
-#ifndef ASTC_PAIRS_PER_THREAD
-#define ASTC_PAIRS_PER_THREAD 4
-#endif
-constexpr int kThreadsPair = ASTC_THREADS_PAIR;
-constexpr int kPairsPerThread = ASTC_PAIRS_PER_THREAD;
-
-struct PairSmem {
-    float4 tex[16][kThreadsPair];                 // block A's UNORM texels during the paired power iteration
-    uint4 rows[2][4][kThreadsPair];               // cp.async landing slots: [A|B][texel row][thread]
-    dev::SharedTables st;
-};
-
-__device__ __forceinline__ void cp_async16(uint32_t saddr, const void *g)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
-}
-
-struct Pending {
-    uint4 *out;
-    bool fast;       // rows are in the cp.async slot; otherwise per-texel loads at use (edge / unaligned block)
-    bool store;      // false: the id was past the end, the slot re-encodes the partner block and drops the result
-};
-
-// Start fetching block `id` into slot `which`; ids past the end fall back to `fallback_id` (always valid).
-template <bool BATCH>
-__device__ __forceinline__ Pending prefetch_block(const EncodeParams &p, uint64_t &id, uint64_t fallback_id, uint32_t slot)
-{
-    Located loc;
-    Pending pd;
-    pd.store = locate<BATCH>(p, id, loc);
-    if (!pd.store) {
-        id = fallback_id;
-        locate<BATCH>(p, id, loc);
-    }
-    pd.out = loc.out;
-    const int x0 = loc.bx * 4, y0 = loc.by * 4;
-    pd.fast = (loc.flags & kFlagAligned16) && x0 + 4 <= loc.width && y0 + 4 <= loc.height;
-    if (pd.fast) {
-        const uint8_t *base = loc.rgba + size_t(y0) * loc.pitch + size_t(x0) * 4u;
-#pragma unroll
-        for (int r = 0; r < 4; ++r) cp_async16(slot + uint32_t(r) * (kThreadsPair * 16u), base + size_t(r) * loc.pitch);
-    }
-    return pd;
-}
-
-template <bool NORMAL, bool SRGB, bool BATCH>
-__device__ __forceinline__ void load_texels4x4(const EncodeParams &p, uint64_t id, bool fast, const uint4 *slot,
-                                               const float *lut_rgb, Texels4x4 &tx, f2 &sum_lo, f2 &sum_hi)
-{
-    sum_lo = dev::bc(0.f);
-    sum_hi = dev::bc(0.f);
-    if (fast) {
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const uint4 row = slot[r * kThreadsPair];
-            tx.t[4 * r + 0] = convert_texel<SRGB, NORMAL>(row.x, lut_rgb, sum_lo, sum_hi);
-            tx.t[4 * r + 1] = convert_texel<SRGB, NORMAL>(row.y, lut_rgb, sum_lo, sum_hi);
-            tx.t[4 * r + 2] = convert_texel<SRGB, NORMAL>(row.z, lut_rgb, sum_lo, sum_hi);
-            tx.t[4 * r + 3] = convert_texel<SRGB, NORMAL>(row.w, lut_rgb, sum_lo, sum_hi);
-        }
-    } else {
-        // edge / unaligned: per-texel loads, out-of-range texels read as 0 like Texture2D.Load
-        // (ASTC_Encode.hlsl:574); the UNORM / sRGB value of byte 0 is 0.
-        Located cur;
-        locate<BATCH>(p, id, cur);
-        const int x0 = cur.bx * 4, y0 = cur.by * 4;
-        const uint8_t *base = cur.rgba + size_t(y0) * cur.pitch + size_t(x0) * 4u;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const int x = x0 + (k & 3), y = y0 + (k >> 2);
-            const bool inside = x < cur.width && y < cur.height;
-            const uint32_t w = inside ? __ldg((const uint32_t *)(base + size_t(k >> 2) * cur.pitch + size_t(k & 3) * 4u)) : 0u;
-            tx.t[k] = convert_texel<SRGB, NORMAL>(w, lut_rgb, sum_lo, sum_hi);
-        }
-    }
-}
-
-template <bool ALPHA, bool NORMAL, bool SRGB, bool BATCH>
-__global__ void __launch_bounds__(kThreadsPair, ASTC_MINBLOCKS_PAIR)
-encode4x4_pair_kernel(const EncodeParams p)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    PairSmem &sm = *reinterpret_cast<PairSmem *>(smem_raw);
-    load_shared_tables<ALPHA, SRGB>(sm.st);
-    __syncthreads();
-    const uint32_t s_field = smem_addr(sm.st.field), s_trit = smem_addr(sm.st.trit_scattered);
-    const uint32_t slot_a = smem_addr(&sm.rows[0][0][threadIdx.x]), slot_b = smem_addr(&sm.rows[1][0][threadIdx.x]);
-    float4 *const park = &sm.tex[0][threadIdx.x];
-
-    // CTA b owns ids [b*2*PAIRS*T, (b+1)*2*PAIRS*T); pair q of a thread is the q-th two runs of T
-    // consecutive ids, so a warp still reads 512 contiguous bytes per texel row and stores 512.
-    uint64_t id_a = uint64_t(blockIdx.x) * (2 * kPairsPerThread * kThreadsPair) + threadIdx.x;
-    if (id_a >= p.total_blocks) return;
-    uint64_t id_b = id_a + kThreadsPair;
-    Pending pa = prefetch_block<BATCH>(p, id_a, id_a, slot_a);
-    Pending pb = prefetch_block<BATCH>(p, id_b, id_a, slot_b);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-
-#pragma unroll 1
-    for (int pair = 0;; ++pair) {
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        f2 sum_lo, sum_hi;
-        // ---- block A: texels -> statistics; texels parked in shared memory ----
-        dev::BlockStats sa;
-        {
-            Texels4x4 ta;
-            load_texels4x4<NORMAL, SRGB, BATCH>(p, id_a, pa.fast, &sm.rows[0][0][threadIdx.x], sm.st.lut_rgb, ta, sum_lo, sum_hi);
-            sa = dev::block_stats<4, NORMAL>(ta, sum_lo, sum_hi);
-#pragma unroll
-            for (int k = 0; k < 16; ++k) park[k * kThreadsPair] = make_float4(ta.t[k].lo.x, ta.t[k].lo.y, ta.t[k].hi.x, ta.t[k].hi.y);
-        }
-        // ---- block B: texels stay in registers ----
-        Texels4x4 tb;
-        load_texels4x4<NORMAL, SRGB, BATCH>(p, id_b, pb.fast, &sm.rows[1][0][threadIdx.x], sm.st.lut_rgb, tb, sum_lo, sum_hi);
-        const dev::BlockStats sb = dev::block_stats<4, NORMAL>(tb, sum_lo, sum_hi);
-
-        // ---- the next pair's rows start their trip now (both slots have been consumed) ----
-        uint4 *const out_a = pa.out, *const out_b = pb.out;
-        const bool store_b = pb.store;
-        bool more = pair + 1 < kPairsPerThread && store_b;
-        if (more) {
-            const uint64_t next_a = id_a + 2 * kThreadsPair;
-            more = next_a < p.total_blocks;
-            if (more) {
-                id_a = next_a;
-                id_b = next_a + kThreadsPair;
-                pa = prefetch_block<BATCH>(p, id_a, id_a, slot_a);
-                pb = prefetch_block<BATCH>(p, id_b, id_a, slot_b);
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-
-        // ---- both principal axes in lock step ----
-        f2 axa_lo, axa_hi, axb_lo, axb_hi;
-        dev::power_iteration_pair<NORMAL>(sa.m, sb.m, axa_lo, axa_hi, axb_lo, axb_hi);
-
-        // ---- finish B from registers, then A from its parked texels ----
-        const uint4 blk_b = dev::finish_block<4, ALPHA, NORMAL>(tb, sb.mean_lo, sb.mean_hi, axb_lo, axb_hi, s_field, s_trit);
-        if (store_b) *out_b = blk_b;
-        {
-            Texels4x4 ta;
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const float4 v = park[k * kThreadsPair];
-                ta.t[k] = Texel{dev::mk(v.x, v.y), dev::mk(v.z, v.w)};
-            }
-            *out_a = dev::finish_block<4, ALPHA, NORMAL>(ta, sa.mean_lo, sa.mean_hi, axa_lo, axa_hi, s_field, s_trit);
-        }
-        if (!more) break;
-    }
-}
-#endif  // ASTC_PAIR_4X4
-
-#if ASTC_4X4_SMEM
-// ---------------------------------------------------------------------------
-// 4x4 experiment: texels parked in shared memory (as the 6x6 path does) to free
-// registers for occupancy.
-// ---------------------------------------------------------------------------
-#ifndef ASTC_THREADS_4X4S
-#define ASTC_THREADS_4X4S 128
-#endif
-#ifndef ASTC_MINBLOCKS_4X4S
-#define ASTC_MINBLOCKS_4X4S 5
-#endif
-constexpr int kThreads4x4S = ASTC_THREADS_4X4S;
-
-struct Texels4x4S {
-    const float4 *col;
-    __device__ __forceinline__ Texel raw(int k) const
-    {
-        const float4 v = col[k * kThreads4x4S];
-        return Texel{dev::mk(v.x, v.y), dev::mk(v.z, v.w)};
-    }
-    __device__ __forceinline__ void fence() const { asm volatile("" ::: "memory"); }
-};
-
-template <bool ALPHA, bool NORMAL, bool SRGB, bool BATCH>
-__global__ void __launch_bounds__(kThreads4x4S, ASTC_MINBLOCKS_4X4S)
-encode4x4s_kernel(const EncodeParams p)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4 *s_tex = reinterpret_cast<float4 *>(smem_raw);                   // [16][kThreads4x4S]
-    dev::SharedTables &st = *reinterpret_cast<dev::SharedTables *>(s_tex + 16 * kThreads4x4S);
-    load_shared_tables<ALPHA, SRGB>(st);
-    __syncthreads();
-    const uint32_t s_field = smem_addr(st.field), s_trit = smem_addr(st.trit_scattered);
-    float4 *col = s_tex + threadIdx.x;
-
-    uint64_t id = uint64_t(blockIdx.x) * (kBlocksPerThread4x4 * kThreads4x4S) + threadIdx.x;
-    Located loc;
-    Rows4x4 rows;
-    bool valid = locate<BATCH>(p, id, loc);
-    if (valid) fetch_rows(loc, rows);
-#pragma unroll 1
-    for (int pass = 0; pass < kBlocksPerThread4x4 && valid; ++pass) {
-        const Located cur = loc;
-        const Rows4x4 now = rows;
-        f2 sum_lo = dev::bc(0.f), sum_hi = dev::bc(0.f);
-        auto park = [&](int k, uint32_t w) {
-            const Texel t = convert_texel<SRGB, NORMAL>(w, st.lut_rgb, sum_lo, sum_hi);
-            col[k * kThreads4x4S] = make_float4(t.lo.x, t.lo.y, t.hi.x, t.hi.y);
-        };
-        if (now.fast) {
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                park(4 * r + 0, now.r[r].x); park(4 * r + 1, now.r[r].y);
-                park(4 * r + 2, now.r[r].z); park(4 * r + 3, now.r[r].w);
-            }
-        } else {
-            const int x0 = cur.bx * 4, y0 = cur.by * 4;
-            const uint8_t *base = cur.rgba + size_t(y0) * cur.pitch + size_t(x0) * 4u;
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const int x = x0 + (k & 3), y = y0 + (k >> 2);
-                const bool inside = x < cur.width && y < cur.height;
-                park(k, inside ? __ldg((const uint32_t *)(base + size_t(k >> 2) * cur.pitch + size_t(k & 3) * 4u)) : 0u);
-            }
-        }
-        if (pass + 1 < kBlocksPerThread4x4) {              // next block's rows in flight during this encode
-            id += kThreads4x4S;
-            valid = locate<BATCH>(p, id, loc);
-            if (valid) fetch_rows(loc, rows);
-        }
-        Texels4x4S tx{col};
-        *cur.out = dev::encode_block<4, ALPHA, NORMAL>(tx, sum_lo, sum_hi, s_field, s_trit);
-    }
-}
-constexpr size_t kSmem4x4S = size_t(16) * kThreads4x4S * sizeof(float4) + sizeof(dev::SharedTables);
-#endif
 
 // ---------------------------------------------------------------------------
 // 6x6: 36 texels do not fit registers as floats; each thread parks its block
@@ -742,25 +340,27 @@ encode6x6_kernel(const EncodeParams p)
 
     // CTA b owns ids [b*BPT*T, (b+1)*BPT*T); a thread re-uses its own shared-memory column for
     // each of its blocks (only it reads or writes that column: no barrier between passes).
-    uint64_t id = uint64_t(blockIdx.x) * (kBlocksPerThread6x6 * kThreads6x6) + threadIdx.x;
+    Walk<BATCH> wk;
+    if (!wk.start(p, uint64_t(blockIdx.x) * (kBlocksPerThread6x6 * kThreads6x6) + threadIdx.x)) return;
 #pragma unroll 1
-    for (int pass = 0; pass < kBlocksPerThread6x6; ++pass, id += kThreads6x6) {
-        Located loc;
-        if (!locate<BATCH>(p, id, loc)) return;
+    for (int pass = 0;; ++pass) {
         f2 sum_lo = dev::bc(0.f), sum_hi = dev::bc(0.f);
-        const int x0 = loc.bx * 6, y0 = loc.by * 6;
-        const uint8_t *base = loc.rgba + size_t(y0) * loc.pitch + size_t(x0) * 4u;
+        const ImageDesc &d = wk.desc(p);
+        const uint32_t x0 = wk.bx * 6u, y0 = wk.by * 6u;
+        const size_t pitch = d.pitch;
+        const uint32_t width = uint32_t(d.width), height = uint32_t(d.height);
+        const uint8_t *base = d.rgba + size_t(y0) * pitch + size_t(x0) * 4u;
         auto park = [&](int k, uint32_t w) {
             const Texel t = convert_texel<SRGB, NORMAL>(w, st.lut_rgb, sum_lo, sum_hi);
             col[k * kThreads6x6] = make_float4(t.lo.x, t.lo.y, t.hi.x, t.hi.y);
         };
-        if ((loc.flags & kFlagAligned8) && x0 + 6 <= loc.width && y0 + 6 <= loc.height) {
+        if ((d.flags & kFlagAligned8) && x0 + 6u <= width && y0 + 6u <= height) {
             // interior: a block row is 24 B = three 8-byte loads; a warp covers 768
             // contiguous bytes per texel row.  All 18 loads are issued before the first use.
             uint2 rows[18];
 #pragma unroll
             for (int r = 0; r < 6; ++r) {
-                const uint2 *src = (const uint2 *)(base + size_t(r) * loc.pitch);
+                const uint2 *src = (const uint2 *)(base + size_t(r) * pitch);
                 rows[3 * r + 0] = __ldg(src); rows[3 * r + 1] = __ldg(src + 1); rows[3 * r + 2] = __ldg(src + 2);
             }
 #pragma unroll
@@ -768,14 +368,15 @@ encode6x6_kernel(const EncodeParams p)
         } else {
 #pragma unroll 6
             for (int k = 0; k < 36; ++k) {
-                const int kx = k % 6, ky = k / 6;
-                const bool inside = x0 + kx < loc.width && y0 + ky < loc.height;
-                park(k, inside ? __ldg((const uint32_t *)(base + size_t(ky) * loc.pitch + size_t(kx) * 4u)) : 0u);
+                const uint32_t kx = k % 6, ky = k / 6;
+                const bool inside = x0 + kx < width && y0 + ky < height;
+                park(k, inside ? __ldg((const uint32_t *)(base + size_t(ky) * pitch + size_t(kx) * 4u)) : 0u);
             }
         }
         if (NORMAL) sum_hi = dev::bc(36.0f * 255.0f);
         Texels6x6 tx{col};
-        *loc.out = dev::encode_block<6, ALPHA, NORMAL>(tx, sum_lo, sum_hi, s_field, s_trit);
+        *wk.out(p) = dev::encode_block<6, ALPHA, NORMAL>(tx, sum_lo, sum_hi, s_field, s_trit);
+        if (pass + 1 >= kBlocksPerThread6x6 || !wk.advance(p, kThreads6x6)) break;
     }
 }
 
@@ -788,43 +389,10 @@ template <bool ALPHA, bool NORMAL, bool SRGB, bool BATCH>
 static cudaError_t launch_variant(int dim, const EncodeParams &p, cudaStream_t stream)
 {
     if (dim == 4) {
-#if ASTC_TEX_4X4
-        if (!SRGB && p.all_textured) {
-            constexpr uint64_t per_cta = uint64_t(kThreads4x4) * kBlocksPerThread4x4;
-            const uint64_t ctas = (p.total_blocks + per_cta - 1) / per_cta;
-            if (ctas > 0x7FFFFFFFull) return cudaErrorInvalidConfiguration;
-            encode4x4_tex_kernel<ALPHA, NORMAL, BATCH><<<unsigned(ctas), kThreads4x4, 0, stream>>>(p);
-            return cudaGetLastError();
-        }
-#endif
-#if ASTC_4X4_SMEM
-        constexpr uint64_t per_cta = uint64_t(kThreads4x4S) * kBlocksPerThread4x4;
-        const uint64_t ctas = (p.total_blocks + per_cta - 1) / per_cta;
-        if (ctas > 0x7FFFFFFFull) return cudaErrorInvalidConfiguration;
-        auto kern = encode4x4s_kernel<ALPHA, NORMAL, SRGB, BATCH>;
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmem4x4S));
-        if (e != cudaSuccess) return e;
-        kern<<<unsigned(ctas), kThreads4x4S, kSmem4x4S, stream>>>(p);
-#elif ASTC_PAIR_4X4
-        constexpr uint64_t per_cta = uint64_t(kThreadsPair) * 2 * kPairsPerThread;
-        const uint64_t ctas = (p.total_blocks + per_cta - 1) / per_cta;
-        if (ctas > 0x7FFFFFFFull) return cudaErrorInvalidConfiguration;
-        auto kern = encode4x4_pair_kernel<ALPHA, NORMAL, SRGB, BATCH>;
-        static thread_local int configured_device4 = -1;
-        int devno4 = 0;
-        cudaGetDevice(&devno4);
-        if (configured_device4 != devno4) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(PairSmem)));
-            if (e != cudaSuccess) return e;
-            configured_device4 = devno4;
-        }
-        kern<<<unsigned(ctas), kThreadsPair, sizeof(PairSmem), stream>>>(p);
-#else
         constexpr uint64_t per_cta = uint64_t(kThreads4x4) * kBlocksPerThread4x4;
         const uint64_t ctas = (p.total_blocks + per_cta - 1) / per_cta;
         if (ctas > 0x7FFFFFFFull) return cudaErrorInvalidConfiguration;
         encode4x4_kernel<ALPHA, NORMAL, SRGB, BATCH><<<unsigned(ctas), kThreads4x4, 0, stream>>>(p);
-#endif
     } else {
         constexpr uint64_t per_cta6 = uint64_t(kThreads6x6) * kBlocksPerThread6x6;
         const uint64_t ctas = (p.total_blocks + per_cta6 - 1) / per_cta6;

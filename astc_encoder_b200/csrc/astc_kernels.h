@@ -12,11 +12,6 @@ enum : uint32_t {
     kFlagAligned8 = 2u,    // base and pitch are multiples of 8 B  (6x6 vector path)
 };
 
-// Requirements of a pitch-linear 2D texture over the source (cudaDeviceProp::textureAlignment /
-// texturePitchAlignment / maxTexture2DLinear on sm_100).
-constexpr size_t kTexBaseAlign = 512, kTexPitchAlign = 32;
-constexpr int kTexMaxWidth = 131072, kTexMaxHeight = 65000;
-
 // One source texture and its output; what the reference passes through the
 // SRV, UAV and constant buffer (astc_encode.h:107-187).
 struct ImageDesc {
@@ -27,9 +22,6 @@ struct ImageDesc {
     int32_t width, height;
     uint32_t blocks_x;       // xBlockNum (astc_encode.h:127)
     uint32_t flags;
-    unsigned long long tex;  // cudaTextureObject_t over the RGBA8 source (UNORM8 -> float in the texture unit), 0 = none
-    int32_t tex_y0;          // texel row of the texture that is row 0 of this image (bands of one upload share a texture)
-    int32_t reserved;
 };
 
 struct EncodeParams {
@@ -37,7 +29,6 @@ struct EncodeParams {
     const ImageDesc *table;      // device array, sorted by first_block
     int32_t count;
     uint64_t total_blocks;
-    uint32_t all_textured;       // every image carries a texture object: the texture-fetch kernels may run
 };
 
 cudaError_t launch_encode(int dim, bool alpha, bool normal, bool srgb, const EncodeParams &p, cudaStream_t stream);
