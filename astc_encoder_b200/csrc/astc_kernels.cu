@@ -213,7 +213,7 @@ struct Texels4x4 {
 #define ASTC_THREADS_4X4 128
 #endif
 #ifndef ASTC_MINBLOCKS_4X4
-#define ASTC_MINBLOCKS_4X4 3
+#define ASTC_MINBLOCKS_4X4 4
 #endif
 #ifndef ASTC_BPT_4X4
 #define ASTC_BPT_4X4 8
