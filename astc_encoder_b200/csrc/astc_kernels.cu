@@ -33,6 +33,8 @@ __device__ const dev::LutImage g_srgb_lut = {{
 #include "srgb_lut.inc"
 }};
 
+__device__ const dev::LutImage g_unorm_lut = dev::make_unorm_lut();
+
 const float *host_srgb_lut() { return h_srgb_lut; }
 
 using dev::f2;
@@ -73,26 +75,41 @@ __device__ __forceinline__ f2 bytes_hi(uint32_t w)
     return dev::add2(dev::mk(byte_bits<2>(w), byte_bits<3>(w)), dev::bc(-8388608.0f));
 }
 
-// sRGB LUT entry of byte SEL: one PRMT (zero-extended byte), one IMAD for the address, one LDS.
+// LUT entry of byte SEL of a packed texel: two ALU-pipe ops for the address, one LDS.
 template <int SEL>
-__device__ __forceinline__ float lut_at(const float *lut_rgb, uint32_t w)
+__device__ __forceinline__ float lut_at(const float *lut, uint32_t w)
 {
     const uint32_t b = __byte_perm(w, 0u, 0x4440 | SEL);
     float v;
-    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(b * 4u + uint32_t(__cvta_generic_to_shared(lut_rgb))));
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(b * 4u + uint32_t(__cvta_generic_to_shared(lut))));
     return v;
 }
 
-// One texel: UNORM floats + its contribution texel*255 to the mean's running sum
-// (ASTC_Encode.hlsl:142-147, 565-580).  Linear: RN(raw*255) == c exactly for every
-// byte, so the sum adds the byte values themselves.  sRGB: rgb come from the LUT
-// and the product is rounded (scalar FMUL) before the add; alpha is never
+// One texel: its channel values (UNORM floats, rgb sRGB-decoded for -srgb) + its contribution
+// texel*255 to the mean's running sum (ASTC_Encode.hlsl:142-147, 565-580).
+//
+// The values come from 256-entry tables in shared memory.  Computing c/255 costs the FP32 pipe
+// -- the kernel's busiest -- four packed operations per texel; a lookup costs it none (address
+// arithmetic runs on the ALU pipe, the load on the LSU) and returns the same bits.
+// Sum, linear channels: RN(raw*255) == c for every byte, and the running sum of bytes is an exact
+// integer below 2^14, so fma(raw, 255, sum) == sum + c == the reference's rounded product plus
+// add.  sRGB channels: the product is rounded (scalar FMUL) before the add.  Alpha is never
 // sRGB-decoded.  NORMAL: b = a = 1.0 (:575-578), handled by the caller as constants.
-template <bool SRGB, bool NORMAL>
-__device__ __forceinline__ Texel convert_texel(uint32_t w, const float *lut_rgb, f2 &sum_lo, f2 &sum_hi)
+// LUT = false (the 6x6 kernel, whose shared-memory pipe is the busy one): linear channels are
+// computed (byte splice + c/255 as FMUL + FFMA) and only the sRGB decode is looked up.
+template <bool SRGB, bool NORMAL, bool LUT>
+__device__ __forceinline__ Texel convert_texel(uint32_t w, const float *lut_rgb, const float *lut_a, f2 &sum_lo, f2 &sum_hi)
 {
     Texel t;
-    if (!SRGB) {
+    const f2 k255 = dev::bc(255.0f);
+    if (!SRGB && LUT) {
+        t.lo = dev::mk(lut_at<0>(lut_rgb, w), lut_at<1>(lut_rgb, w));
+        sum_lo = dev::fma2(t.lo, k255, sum_lo);
+        if (!NORMAL) {
+            t.hi = dev::mk(lut_at<2>(lut_rgb, w), lut_at<3>(lut_rgb, w));
+            sum_hi = dev::fma2(t.hi, k255, sum_hi);
+        }
+    } else if (!SRGB) {
         const f2 clo = bytes_lo(w);
         t.lo = unorm2(clo);
         sum_lo = dev::add2(sum_lo, clo);
@@ -105,9 +122,14 @@ __device__ __forceinline__ Texel convert_texel(uint32_t w, const float *lut_rgb,
         t.lo = dev::mk(lut_at<0>(lut_rgb, w), lut_at<1>(lut_rgb, w));
         sum_lo = dev::add2(sum_lo, dev::mk(dev::fmul(t.lo.x, 255.0f), dev::fmul(t.lo.y, 255.0f)));
         if (!NORMAL) {
-            const float ca = dev::fsub(byte_bits<3>(w), 8388608.0f);
-            t.hi = dev::mk(lut_at<2>(lut_rgb, w), unorm1(ca));
-            sum_hi = dev::add2(sum_hi, dev::mk(dev::fmul(t.hi.x, 255.0f), ca));
+            if (LUT) {
+                t.hi = dev::mk(lut_at<2>(lut_rgb, w), lut_at<3>(lut_a, w));
+                sum_hi = dev::mk(dev::fadd(sum_hi.x, dev::fmul(t.hi.x, 255.0f)), dev::ffma(t.hi.y, 255.0f, sum_hi.y));
+            } else {
+                const float ca = dev::fsub(byte_bits<3>(w), 8388608.0f);
+                t.hi = dev::mk(lut_at<2>(lut_rgb, w), unorm1(ca));
+                sum_hi = dev::add2(sum_hi, dev::mk(dev::fmul(t.hi.x, 255.0f), ca));
+            }
         }
     }
     if (NORMAL) t.hi = dev::bc(1.0f);
@@ -184,18 +206,25 @@ struct Walk {
     }
 };
 
-template <bool ALPHA, bool SRGB>
+template <bool ALPHA, bool SRGB, bool UNORM_LUT>
 __device__ __forceinline__ void load_shared_tables(dev::SharedTables &st)
 {
     static_assert(sizeof(dev::TableImage) % 16 == 0 && offsetof(dev::SharedTables, lut_rgb) == sizeof(dev::TableImage), "table layout");
     const uint4 *src = reinterpret_cast<const uint4 *>(ALPHA ? &g_tables_q6 : &g_tables_q12);
     uint4 *dst = reinterpret_cast<uint4 *>(&st);
     for (int i = threadIdx.x; i < int(sizeof(dev::TableImage) / 16); i += blockDim.x) dst[i] = __ldg(src + i);
-    if (SRGB) {
-        const uint4 *lsrc = reinterpret_cast<const uint4 *>(&g_srgb_lut);
+    if (SRGB || UNORM_LUT) {
+        const uint4 *lsrc = reinterpret_cast<const uint4 *>(SRGB ? &g_srgb_lut : &g_unorm_lut);
         uint4 *ldst = reinterpret_cast<uint4 *>(st.lut_rgb);
         for (int i = threadIdx.x; i < 64; i += blockDim.x) ldst[i] = __ldg(lsrc + i);
     }
+}
+
+__device__ __forceinline__ void load_alpha_lut(float *lut_a)
+{
+    const uint4 *asrc = reinterpret_cast<const uint4 *>(&g_unorm_lut);
+    uint4 *adst = reinterpret_cast<uint4 *>(lut_a);
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) adst[i] = __ldg(asrc + i);
 }
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return uint32_t(__cvta_generic_to_shared(p)); }
@@ -254,7 +283,9 @@ encode4x4_kernel(const EncodeParams p)
 {
     __shared__ dev::SharedTables st;
     __shared__ uint4 s_rows[2][4][kThreads4x4];                 // cp.async landing slots, double-buffered
-    load_shared_tables<ALPHA, SRGB>(st);
+    __shared__ __align__(16) float s_lut_a[SRGB ? 256 : 4];
+    load_shared_tables<ALPHA, SRGB, true>(st);
+    if (SRGB) load_alpha_lut(s_lut_a);
     __syncthreads();
     const uint32_t s_field = smem_addr(st.field), s_trit = smem_addr(st.trit_scattered);
     const uint32_t slot0 = smem_addr(&s_rows[0][0][threadIdx.x]);
@@ -274,10 +305,10 @@ encode4x4_kernel(const EncodeParams p)
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
                 const uint4 row = s_rows[pass & 1][r][threadIdx.x];
-                tx.t[4 * r + 0] = convert_texel<SRGB, NORMAL>(row.x, st.lut_rgb, sum_lo, sum_hi);
-                tx.t[4 * r + 1] = convert_texel<SRGB, NORMAL>(row.y, st.lut_rgb, sum_lo, sum_hi);
-                tx.t[4 * r + 2] = convert_texel<SRGB, NORMAL>(row.z, st.lut_rgb, sum_lo, sum_hi);
-                tx.t[4 * r + 3] = convert_texel<SRGB, NORMAL>(row.w, st.lut_rgb, sum_lo, sum_hi);
+                tx.t[4 * r + 0] = convert_texel<SRGB, NORMAL, true>(row.x, st.lut_rgb, s_lut_a, sum_lo, sum_hi);
+                tx.t[4 * r + 1] = convert_texel<SRGB, NORMAL, true>(row.y, st.lut_rgb, s_lut_a, sum_lo, sum_hi);
+                tx.t[4 * r + 2] = convert_texel<SRGB, NORMAL, true>(row.z, st.lut_rgb, s_lut_a, sum_lo, sum_hi);
+                tx.t[4 * r + 3] = convert_texel<SRGB, NORMAL, true>(row.w, st.lut_rgb, s_lut_a, sum_lo, sum_hi);
             }
         } else {
             // edge / unaligned: per-texel loads, out-of-range texels read as 0
@@ -291,7 +322,7 @@ encode4x4_kernel(const EncodeParams p)
             for (int k = 0; k < 16; ++k) {
                 const bool inside = x0 + (k & 3) < width && y0 + (k >> 2) < height;
                 const uint32_t w = inside ? __ldg((const uint32_t *)(base + size_t(k >> 2) * pitch + size_t(k & 3) * 4u)) : 0u;
-                tx.t[k] = convert_texel<SRGB, NORMAL>(w, st.lut_rgb, sum_lo, sum_hi);
+                tx.t[k] = convert_texel<SRGB, NORMAL, true>(w, st.lut_rgb, s_lut_a, sum_lo, sum_hi);
             }
         }
         uint4 *const out = wk.out(p);
@@ -333,7 +364,7 @@ encode6x6_kernel(const EncodeParams p)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *s_tex = reinterpret_cast<float4 *>(smem_raw);                   // [36][kThreads6x6]
     dev::SharedTables &st = *reinterpret_cast<dev::SharedTables *>(s_tex + 36 * kThreads6x6);
-    load_shared_tables<ALPHA, SRGB>(st);
+    load_shared_tables<ALPHA, SRGB, false>(st);
     __syncthreads();
     const uint32_t s_field = smem_addr(st.field), s_trit = smem_addr(st.trit_scattered);
     float4 *col = s_tex + threadIdx.x;
@@ -351,7 +382,7 @@ encode6x6_kernel(const EncodeParams p)
         const uint32_t width = uint32_t(d.width), height = uint32_t(d.height);
         const uint8_t *base = d.rgba + size_t(y0) * pitch + size_t(x0) * 4u;
         auto park = [&](int k, uint32_t w) {
-            const Texel t = convert_texel<SRGB, NORMAL>(w, st.lut_rgb, sum_lo, sum_hi);
+            const Texel t = convert_texel<SRGB, NORMAL, false>(w, st.lut_rgb, nullptr, sum_lo, sum_hi);
             col[k * kThreads6x6] = make_float4(t.lo.x, t.lo.y, t.hi.x, t.hi.y);
         };
         if ((d.flags & kFlagAligned8) && x0 + 6u <= width && y0 + 6u <= height) {
