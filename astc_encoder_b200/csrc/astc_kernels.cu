@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include <cstddef>
+#include <cstdlib>
 
 #include "astc_block.cuh"
 
@@ -244,11 +245,8 @@ struct Texels4x4 {
 #ifndef ASTC_MINBLOCKS_4X4
 #define ASTC_MINBLOCKS_4X4 4
 #endif
-#ifndef ASTC_BPT_4X4
-#define ASTC_BPT_4X4 8
-#endif
 constexpr int kThreads4x4 = ASTC_THREADS_4X4;
-constexpr int kBlocksPerThread4x4 = ASTC_BPT_4X4;   // ASTC blocks each thread encodes, one after the other
+constexpr int kMaxPasses = 8;  // most blocks a thread encodes one after the other
 
 // The four 16-byte texel rows of the thread's next block travel global -> shared memory by
 // cp.async (LDGSTS) while the current block is being encoded: the copy holds no registers
@@ -294,7 +292,7 @@ encode4x4_kernel(const EncodeParams p)
     // CTA b owns ids [b*BPT*T, (b+1)*BPT*T); pass i takes the i-th run of T consecutive ids, so a
     // warp reads 512 contiguous bytes per texel row and stores 512 contiguous bytes.
     Walk<BATCH> wk;
-    if (!wk.start(p, uint64_t(blockIdx.x) * (kBlocksPerThread4x4 * kThreads4x4) + threadIdx.x)) return;
+    if (!wk.start(p, uint64_t(blockIdx.x) * uint32_t(p.passes * kThreads4x4) + threadIdx.x)) return;
     bool fast = prefetch_rows4x4<BATCH>(p, wk, slot0);
 #pragma unroll 1
     for (int pass = 0;; ++pass) {
@@ -326,7 +324,7 @@ encode4x4_kernel(const EncodeParams p)
             }
         }
         uint4 *const out = wk.out(p);
-        const bool more = pass + 1 < kBlocksPerThread4x4 && wk.advance(p, kThreads4x4);
+        const bool more = pass + 1 < p.passes && wk.advance(p, kThreads4x4);
         if (more) fast = prefetch_rows4x4<BATCH>(p, wk, slot0 + uint32_t((pass + 1) & 1) * kSlotStride);
         // one coalesced 16-byte store per thread
         *out = dev::encode_block<4, ALPHA, NORMAL>(tx, sum_lo, sum_hi, s_field, s_trit);
@@ -341,11 +339,7 @@ encode4x4_kernel(const EncodeParams p)
 #ifndef ASTC_THREADS_6X6
 #define ASTC_THREADS_6X6 128
 #endif
-#ifndef ASTC_BPT_6X6
-#define ASTC_BPT_6X6 4
-#endif
 constexpr int kThreads6x6 = ASTC_THREADS_6X6;
-constexpr int kBlocksPerThread6x6 = ASTC_BPT_6X6;
 
 struct Texels6x6 {
     const float4 *col;                                    // &smem[threadIdx.x], stride kThreads6x6
@@ -372,7 +366,7 @@ encode6x6_kernel(const EncodeParams p)
     // CTA b owns ids [b*BPT*T, (b+1)*BPT*T); a thread re-uses its own shared-memory column for
     // each of its blocks (only it reads or writes that column: no barrier between passes).
     Walk<BATCH> wk;
-    if (!wk.start(p, uint64_t(blockIdx.x) * (kBlocksPerThread6x6 * kThreads6x6) + threadIdx.x)) return;
+    if (!wk.start(p, uint64_t(blockIdx.x) * uint32_t(p.passes * kThreads6x6) + threadIdx.x)) return;
 #pragma unroll 1
     for (int pass = 0;; ++pass) {
         f2 sum_lo = dev::bc(0.f), sum_hi = dev::bc(0.f);
@@ -407,7 +401,7 @@ encode6x6_kernel(const EncodeParams p)
         if (NORMAL) sum_hi = dev::bc(36.0f * 255.0f);
         Texels6x6 tx{col};
         *wk.out(p) = dev::encode_block<6, ALPHA, NORMAL>(tx, sum_lo, sum_hi, s_field, s_trit);
-        if (pass + 1 >= kBlocksPerThread6x6 || !wk.advance(p, kThreads6x6)) break;
+        if (pass + 1 >= p.passes || !wk.advance(p, kThreads6x6)) break;
     }
 }
 
@@ -416,16 +410,37 @@ constexpr size_t kSmem6x6 = size_t(36) * kThreads6x6 * sizeof(float4) + sizeof(d
 // ---------------------------------------------------------------------------
 // launch
 // ---------------------------------------------------------------------------
+// Blocks per thread.  More passes amortise the per-CTA table load and the first, unprefetched block
+// (4x4, 16384^2: 0.87 ms at 1 pass, 0.78 at 2, 0.75 at 4, 0.736 at 8), but the grid should keep about
+// three waves of resident CTAs or the last partial wave idles the SMs (4096^2 is best at 4 passes).
+// The 6x6 kernel has no prefetch to amortise and is best at 1-3 passes (measured on 8192^2).
+static int choose_passes(uint64_t total_blocks, int threads, int ctas_per_sm, int max_passes)
+{
+    static thread_local int sm_count = 0;
+    if (sm_count == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+            sm_count = 148;
+    }
+    const char *force = getenv("ASTC_B200_PASSES");                       // tuning hook (tools/passes_sweep.sh)
+    if (force && atoi(force) > 0) return atoi(force) > kMaxPasses ? kMaxPasses : atoi(force);
+    const uint64_t resident = uint64_t(sm_count) * uint64_t(ctas_per_sm);
+    const uint64_t want = total_blocks / (resident * 3u * uint64_t(threads));
+    return want < 1 ? 1 : want > uint64_t(max_passes) ? max_passes : int(want);
+}
+
 template <bool ALPHA, bool NORMAL, bool SRGB, bool BATCH>
-static cudaError_t launch_variant(int dim, const EncodeParams &p, cudaStream_t stream)
+static cudaError_t launch_variant(int dim, EncodeParams p, cudaStream_t stream)
 {
     if (dim == 4) {
-        constexpr uint64_t per_cta = uint64_t(kThreads4x4) * kBlocksPerThread4x4;
+        p.passes = choose_passes(p.total_blocks, kThreads4x4, ASTC_MINBLOCKS_4X4, kMaxPasses);
+        const uint64_t per_cta = uint64_t(kThreads4x4) * uint64_t(p.passes);
         const uint64_t ctas = (p.total_blocks + per_cta - 1) / per_cta;
         if (ctas > 0x7FFFFFFFull) return cudaErrorInvalidConfiguration;
         encode4x4_kernel<ALPHA, NORMAL, SRGB, BATCH><<<unsigned(ctas), kThreads4x4, 0, stream>>>(p);
     } else {
-        constexpr uint64_t per_cta6 = uint64_t(kThreads6x6) * kBlocksPerThread6x6;
+        p.passes = choose_passes(p.total_blocks, kThreads6x6, 3, 2);
+        const uint64_t per_cta6 = uint64_t(kThreads6x6) * uint64_t(p.passes);
         const uint64_t ctas = (p.total_blocks + per_cta6 - 1) / per_cta6;
         if (ctas > 0x7FFFFFFFull) return cudaErrorInvalidConfiguration;
         auto kern = encode6x6_kernel<ALPHA, NORMAL, SRGB, BATCH>;

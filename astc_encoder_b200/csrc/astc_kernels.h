@@ -29,6 +29,7 @@ struct EncodeParams {
     const ImageDesc *table;      // device array, sorted by first_block
     int32_t count;
     uint64_t total_blocks;
+    int32_t passes;              // blocks each thread encodes one after the other (set by launch_encode)
 };
 
 cudaError_t launch_encode(int dim, bool alpha, bool normal, bool srgb, const EncodeParams &p, cudaStream_t stream);
