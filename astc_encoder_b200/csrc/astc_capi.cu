@@ -384,7 +384,7 @@ uint32_t astc_b200_blockmode(int weight_quant) { return astc::blockmode_4x4grid(
 int astc_b200_unorm_lut(int srgb, float out[256])
 {
     if (!out) return ASTC_B200_ERR_INVALID_ARGUMENT;
-    for (int c = 0; c < 256; ++c) out[c] = srgb ? astc::host_srgb_lut()[c] : float(c) / 255.0f;
+    for (int c = 0; c < 256; ++c) out[c] = srgb ? astc::host_srgb_lut()[c] : astc::host_unorm_lut()[c];
     return ASTC_B200_OK;
 }
 

@@ -35,8 +35,10 @@ __device__ const dev::LutImage g_srgb_lut = {{
 }};
 
 __device__ const dev::LutImage g_unorm_lut = dev::make_unorm_lut();
+static const dev::LutImage h_unorm_lut = dev::make_unorm_lut();     // same constexpr generator, host copy for tests
 
 const float *host_srgb_lut() { return h_srgb_lut; }
+const float *host_unorm_lut() { return h_unorm_lut.v; }
 
 using dev::f2;
 using dev::Texel;
@@ -336,6 +338,9 @@ encode4x4_kernel(const EncodeParams p)
 // 6x6: 36 texels do not fit registers as floats; each thread parks its block
 // as float4[36] in its own shared-memory column (conflict-free: bank = lane).
 // ---------------------------------------------------------------------------
+#ifndef ASTC_L2_PREFETCH_6X6
+#define ASTC_L2_PREFETCH_6X6 1
+#endif
 #ifndef ASTC_THREADS_6X6
 #define ASTC_THREADS_6X6 128
 #endif
@@ -388,6 +393,23 @@ encode6x6_kernel(const EncodeParams p)
                 const uint2 *src = (const uint2 *)(base + size_t(r) * pitch);
                 rows[3 * r + 0] = __ldg(src); rows[3 * r + 1] = __ldg(src + 1); rows[3 * r + 2] = __ldg(src + 2);
             }
+#if ASTC_L2_PREFETCH_6X6
+            // The thread's next block: pull its six rows into L2 now, so the loads above hit L2
+            // instead of HBM one pass later (there is no shared memory left for a cp.async stage
+            // and no registers for a software prefetch).
+            if (pass + 1 < p.passes) {
+                Walk<BATCH> nx = wk;
+                if (nx.advance(p, kThreads6x6)) {
+                    const ImageDesc &dn = nx.desc(p);
+                    const size_t pn = dn.pitch;
+                    const uint8_t *bn = dn.rgba + size_t(nx.by * 6u) * pn + size_t(nx.bx * 6u) * 4u;
+                    if (nx.by * 6u + 6u <= uint32_t(dn.height) && nx.bx * 6u + 6u <= uint32_t(dn.width)) {
+#pragma unroll
+                        for (int r = 0; r < 6; ++r) asm volatile("prefetch.global.L2 [%0];" ::"l"(bn + size_t(r) * pn));
+                    }
+                }
+            }
+#endif
 #pragma unroll
             for (int i = 0; i < 18; ++i) { park(2 * i, rows[i].x); park(2 * i + 1, rows[i].y); }
         } else {

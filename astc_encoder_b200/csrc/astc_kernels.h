@@ -37,5 +37,6 @@ cudaError_t launch_bise(const uint8_t *d_values, int count, int quant, int nseq,
 cudaError_t launch_decode(const uint8_t *d_blocks, int width, int height, int dim, uint8_t *d_rgba, size_t pitch,
                           cudaStream_t stream);
 const float *host_srgb_lut();
+const float *host_unorm_lut();   // the c / 255.0f table the 4x4 kernels look up
 
 }  // namespace astc

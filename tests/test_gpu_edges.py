@@ -157,3 +157,40 @@ def test_leaf_psnr_vs_golden(native, oracle, leaf_rgba, leaf_golden):
     dec_g, _ = oracle.decode_image(leaf_golden[4], 1024, 1024, 4)
     p, pg = oracle.psnr_per_channel(dec, leaf_rgba), oracle.psnr_per_channel(dec_g, leaf_rgba)
     assert np.all(np.abs(p - pg) <= 0.05), (p, pg)
+
+
+@pytest.mark.parametrize("dim", [4, 6])
+@pytest.mark.parametrize("passes", [1, 3, 8])
+def test_block_walk_across_rows_and_passes(native, oracle, dim, passes, monkeypatch):
+    """The incremental block walk (Walk in astc_kernels.cu): widths whose block rows are shorter
+    than, equal to, and not a multiple of the 128-thread stride, under forced pass counts."""
+    import torch
+    monkeypatch.setenv("ASTC_B200_PASSES", str(passes))
+    rng = np.random.default_rng(100 + passes)
+    opt = native.encode_option(is4x4=dim == 4, is6x6=dim == 6, has_alpha=True)
+    for w, h in ((dim * 5, dim * 300), (dim * 128, dim * 17), (dim * 129 - 1, dim * 23 + 1), (dim * 700 + 2, dim * 9)):
+        img = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+        got = _enc(native, torch.from_numpy(img).cuda(), opt)
+        want = oracle.encode_image(img, **_okw(opt, dim))
+        assert np.array_equal(got, want), (w, h, passes)
+
+
+@pytest.mark.parametrize("dim", [4, 6])
+@pytest.mark.parametrize("passes", [1, 8])
+def test_batch_walk_over_many_tiny_images(native, oracle, dim, passes, monkeypatch):
+    """One launch over 150 images from 1x1 to a few hundred texels wide: a thread's next block is
+    often several images further on, so the walk's image-crossing loop and re-division run a lot."""
+    import torch
+    monkeypatch.setenv("ASTC_B200_PASSES", str(passes))
+    rng = np.random.default_rng(7 + passes)
+    sizes = [(int(rng.integers(1, 40)), int(rng.integers(1, 40))) for _ in range(140)] + \
+            [(333, 61), (64, 512), (dim * 128, dim * 3), (1, 1), (2, 700), (517, 3), (dim, dim), (96, 96), (1, 1), (250, 187)]
+    imgs = [rng.integers(0, 256, (h, w, 4), dtype=np.uint8) for w, h in sizes]
+    opt = native.encode_option(is4x4=dim == 4, is6x6=dim == 6)
+    batch = native.Batch([torch.from_numpy(i).cuda() for i in imgs], opt)
+    outs = batch.encode()
+    torch.cuda.synchronize()
+    for img, o in zip(imgs, outs):
+        want = oracle.encode_image(img, **_okw(opt, dim))
+        assert np.array_equal(o.cpu().numpy(), want), img.shape
+    batch.close()

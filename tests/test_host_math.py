@@ -103,3 +103,42 @@ def test_field_table_reconstructs_trit_packing(oracle):
             buf = (C.c_uint8 * 16)()
             L.astc_oracle_bise_encode(qs, 16, method, buf)
             assert int.from_bytes(bytes(buf), "little") == stream
+
+
+def test_fma_sum_of_unorm_texels_is_the_byte_sum():
+    """fma(c/255, 255, sum) == sum + c exactly while sum is an integer below 2^14 (convert_texel,
+    4x4 and 6x6: at most 36 * 255 = 9180): the linear-mode mean may accumulate by FMA."""
+    raw = np.arange(256, dtype=np.float32) / f32(255.0)
+    for c in range(256):
+        prod = Fr(float(raw[c])) * 255                          # the FMA's unrounded product
+        for s in (0, 1, 255, 1023, 2048, 4079, 4096, 8191, 8192, 9180 - c, 16383 - c):
+            assert _rn(prod + s) == f32(s + c), (c, s)
+
+
+def test_trace_bound_decides_the_early_exit():
+    """power_iteration skips the exact |M v|^2 test when fl|M M v|^2 >= 1.02e-10 * trace(M)^2 (and
+    >= 1e-30).  For random Gram matrices in float32 the implication |M v|^2 >= kSmallSq must
+    hold whenever the bound fires -- including matrices scaled down to the threshold."""
+    k = f32(_const(BLOCK, "kSmallSq"))
+    rng = np.random.default_rng(7)
+    fired = 0
+    for trial in range(4000):
+        n = int(rng.integers(2, 37))
+        scale = f32(10.0 ** rng.uniform(-7, 2.5))
+        d = (rng.normal(0, 1, (n, 4)) * np.array([1, rng.uniform(0, 1), rng.uniform(0, 1) ** 4, rng.uniform(0, 1) ** 8])).astype(np.float32) * scale
+        m = np.zeros((4, 4), np.float32)
+        for t in d:                                             # sequential float32 accumulation, like the kernel
+            m = (m + np.outer(t, t).astype(np.float32)).astype(np.float32)
+        m = (m * f32(1.0 / (n - 1))).astype(np.float32)
+        v = rng.normal(0, 1, 4).astype(np.float32)
+        v = (v / np.sqrt(np.sum(v * v, dtype=np.float32))).astype(np.float32)
+        mv = lambda x: np.array([np.float32(sum(f32(m[i, j] * x[j]) for j in range(4))) for i in range(4)], np.float32)
+        u = mv(v)
+        w = mv(u)
+        uu, ww = f32(np.sum(u * u, dtype=np.float32)), f32(np.sum(w * w, dtype=np.float32))
+        tr = f32(m[0, 0] + m[1, 1] + m[2, 2] + m[3, 3])
+        decided = max(f32(f32(tr * tr) * f32(1.02e-10)), f32(1e-30))
+        if ww >= decided:
+            fired += 1
+            assert uu >= k, (trial, uu, ww, tr)
+    assert fired > 1000                                         # the cheap test does decide the common case
