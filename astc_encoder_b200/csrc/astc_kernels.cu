@@ -277,8 +277,11 @@ __device__ __forceinline__ bool prefetch_rows4x4(const EncodeParams &p, const Wa
     return fast;
 }
 
+#ifndef ASTC_MINBLOCKS_4X4_NORMAL
+#define ASTC_MINBLOCKS_4X4_NORMAL 7
+#endif
 template <bool ALPHA, bool NORMAL, bool SRGB, bool BATCH>
-__global__ void __launch_bounds__(kThreads4x4, ASTC_MINBLOCKS_4X4)
+__global__ void __launch_bounds__(kThreads4x4, NORMAL ? ASTC_MINBLOCKS_4X4_NORMAL : ASTC_MINBLOCKS_4X4)
 encode4x4_kernel(const EncodeParams p)
 {
     __shared__ dev::SharedTables st;
@@ -455,7 +458,7 @@ template <bool ALPHA, bool NORMAL, bool SRGB, bool BATCH>
 static cudaError_t launch_variant(int dim, EncodeParams p, cudaStream_t stream)
 {
     if (dim == 4) {
-        p.passes = choose_passes(p.total_blocks, kThreads4x4, ASTC_MINBLOCKS_4X4, kMaxPasses);
+        p.passes = choose_passes(p.total_blocks, kThreads4x4, NORMAL ? ASTC_MINBLOCKS_4X4_NORMAL : ASTC_MINBLOCKS_4X4, kMaxPasses);
         const uint64_t per_cta = uint64_t(kThreads4x4) * uint64_t(p.passes);
         const uint64_t ctas = (p.total_blocks + per_cta - 1) / per_cta;
         if (ctas > 0x7FFFFFFFull) return cudaErrorInvalidConfiguration;
