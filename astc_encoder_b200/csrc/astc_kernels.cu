@@ -430,7 +430,10 @@ encode6x6_kernel(const EncodeParams p)
     }
 }
 
-constexpr size_t kSmem6x6 = size_t(36) * kThreads6x6 * sizeof(float4) + sizeof(dev::SharedTables);
+#ifndef ASTC_EXTRA_SMEM_6X6
+#define ASTC_EXTRA_SMEM_6X6 0            // occupancy experiments only (tools/variants.py)
+#endif
+constexpr size_t kSmem6x6 = size_t(36) * kThreads6x6 * sizeof(float4) + sizeof(dev::SharedTables) + ASTC_EXTRA_SMEM_6X6;
 
 // ---------------------------------------------------------------------------
 // launch
