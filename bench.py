@@ -304,6 +304,20 @@ def run_b200(args) -> int:
 
     peak, peak_src = _peaks()
     achieved = texels * BYTES_PER_TEXEL_4x4 / (kernel_ms * 1e-3) / 1e9
+    # The bound that actually binds: issue slots and the FP32 pipe.  Static per-block instruction counts
+    # come from the committed ncu capture, time and SM clock are this run's.
+    clocks = sampler.summary()
+    sm_hz = float(clocks.get("sm_mhz") or 0) * 1e6
+    smsps = torch.cuda.get_device_properties(0).multi_processor_count * 4
+    instr32, fma32 = _traffic("encode4x4_rgb_warp_instr_per_32_blocks"), _traffic("encode4x4_rgb_fma_pipe_cycles_per_32_blocks")
+    compute = None
+    if instr32 and fma32 and sm_hz > 0:
+        slots = kernel_ms * 1e-3 * sm_hz * smsps                     # issue slots (= FP32-pipe cycles) the launch had
+        warp_blocks = texels / 16 / 32
+        compute = {"bound": "issue / FP32 pipe", "issue_frac": round(instr32 * warp_blocks / slots, 4),
+                   "fma_pipe_frac": round(fma32 * warp_blocks / slots, 4),
+                   "warp_instr_per_32_blocks": instr32, "fma_pipe_cycles_per_32_blocks": fma32,
+                   "note": "1 warp-instruction and 32 FP32 lanes per clock per SMSP; counts from profiles/roofline_traffic.json"}
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
@@ -318,12 +332,12 @@ def run_b200(args) -> int:
                 "link_only_ms": round(link_ms, 3),
                 "note": "PCIe-bound: link_only_ms is the same H2D + D2H traffic with no kernel at all"},
         "gpu_launches": int(launches),
-        "clocks": sampler.summary(),
+        "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": _traffic("encode4x4_rgb"),
                      "kernel": "encode4x4_kernel<rgb,linear>", "kernel_ms": round(kernel_ms, 4),
                      "kernel_ms_best": round(per[0], 4), "algorithmic_bytes_per_launch": int(texels * BYTES_PER_TEXEL_4x4),
-                     "peak_source": peak_src,
+                     "peak_source": peak_src, "compute": compute,
                      "note": "FP32-pipe / register-operand-bandwidth bound (1137 warp-instructions per 32 blocks of 80 B): DESIGN.md 4.1"},
     }
 
