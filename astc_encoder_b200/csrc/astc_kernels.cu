@@ -10,6 +10,7 @@
 
 #include <cstddef>
 #include <cstdlib>
+#include <type_traits>
 
 #include "astc_block.cuh"
 
@@ -236,6 +237,7 @@ __device__ __forceinline__ uint32_t smem_addr(const void *p) { return uint32_t(_
 // 4x4: sixteen texels live in registers as UNORM float pairs.
 // ---------------------------------------------------------------------------
 struct Texels4x4 {
+    static constexpr bool kStreamed = false;
     Texel t[16];
     __device__ __forceinline__ Texel raw(int k) const { return t[k]; }
     __device__ __forceinline__ void fence() const {}
@@ -338,38 +340,76 @@ encode4x4_kernel(const EncodeParams p)
 }
 
 // ---------------------------------------------------------------------------
-// 6x6: 36 texels do not fit registers as floats; each thread parks its block
-// as float4[36] in its own shared-memory column (conflict-free: bank = lane).
+// 6x6: 36 texels (144 floats) do not fit the registers of a thread that is to share its SM with 15
+// other warps.  Each thread parks the first kPark6x6 texels of its block as float4 in its own
+// shared-memory column (bank = lane: conflict-free LDS.128 / STS.128) and keeps the last ten in
+// registers; that is 416 B of shared memory and <= 128 registers per thread, i.e. FOUR 128-thread CTAs
+// per SM.  (All 36 parked and 168 registers -- the first version -- gave three; measured on one box,
+// 8192^2: t = 0.110 + 0.242 / CTAs-per-SM ms, the kernel was latency-bound.)
+//
+// ptxas and the passes over the texels.  Handed a fully unrolled pass it hoists all of its LDS.128 to
+// the top and, short of registers, spills them (800 B of spills measured).  So the covariance and
+// min/max passes run the four texel rows that lie wholly in shared memory as a ROLLED loop and only the
+// tail unrolled (for_each_texel_streamed in astc_block.cuh), and the weight pass, whose 64 taps
+// cannot be rolled, is cut by a scheduling fence every four grid points (__syncwarp: an empty asm
+// never reaches ptxas).  A compiler fence after parking stops NVVM from forwarding the parked values
+// to the covariance pass in registers, which is what used to cost the 168 registers.
+//
+// Normal maps: b = a = 1 for every texel, so only (r, g) is parked (float2) and six CTAs fit.
 // ---------------------------------------------------------------------------
-#ifndef ASTC_L2_PREFETCH_6X6
-#define ASTC_L2_PREFETCH_6X6 1
-#endif
 #ifndef ASTC_THREADS_6X6
 #define ASTC_THREADS_6X6 128
 #endif
 constexpr int kThreads6x6 = ASTC_THREADS_6X6;
+constexpr int kPark6x6 = 26;
+#ifndef ASTC_EXTRA_SMEM_6X6
+#define ASTC_EXTRA_SMEM_6X6 0            // occupancy experiments only (tools/variants.py)
+#endif
 
+template <bool NORMAL>
 struct Texels6x6 {
-    const float4 *col;                                    // &smem[threadIdx.x], stride kThreads6x6
-    __device__ __forceinline__ Texel raw(int k) const
+    using Slot = typename std::conditional<NORMAL, float2, float4>::type;
+    static constexpr bool kStreamed = true;
+    static constexpr int kLoopRows = 4;                   // rows 0..3 (24 texels) are wholly in shared memory
+    Slot *col;                                            // &smem[threadIdx.x], stride kThreads6x6
+    Texel reg[36 - kPark6x6];
+    __device__ __forceinline__ void put(int k, const Texel &t)
     {
-        const float4 v = col[k * kThreads6x6];
-        return Texel{dev::mk(v.x, v.y), dev::mk(v.z, v.w)};
+        if (k >= kPark6x6) reg[k - kPark6x6] = t;
+        else if constexpr (NORMAL) col[k * kThreads6x6] = make_float2(t.lo.x, t.lo.y);
+        else col[k * kThreads6x6] = make_float4(t.lo.x, t.lo.y, t.hi.x, t.hi.y);
     }
+    __device__ __forceinline__ Texel raw_dyn(int k) const
+    {
+        const Slot v = col[k * kThreads6x6];
+        if constexpr (NORMAL) return Texel{dev::mk(v.x, v.y), dev::bc(1.0f)};
+        else return Texel{dev::mk(v.x, v.y), dev::mk(v.z, v.w)};
+    }
+    __device__ __forceinline__ Texel raw(int k) const { return k < kPark6x6 ? raw_dyn(k) : reg[k - kPark6x6]; }
     __device__ __forceinline__ void fence() const { asm volatile("" ::: "memory"); }
+    // a fence ptxas honours when it schedules; the warp is converged wherever this is called
+    __device__ __forceinline__ void sched_fence() const { __syncwarp(); }
 };
 
+template <bool NORMAL>
+constexpr size_t smem6x6()
+{
+    return size_t(kPark6x6) * kThreads6x6 * sizeof(typename Texels6x6<NORMAL>::Slot) + sizeof(dev::SharedTables) + ASTC_EXTRA_SMEM_6X6;
+}
+template <bool NORMAL>
+constexpr int ctas6x6() { return NORMAL ? 6 : 4; }
+
 template <bool ALPHA, bool NORMAL, bool SRGB, bool BATCH>
-__global__ void __launch_bounds__(kThreads6x6, 3)
+__global__ void __launch_bounds__(kThreads6x6, ctas6x6<NORMAL>())
 encode6x6_kernel(const EncodeParams p)
 {
+    using TX = Texels6x6<NORMAL>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4 *s_tex = reinterpret_cast<float4 *>(smem_raw);                   // [36][kThreads6x6]
-    dev::SharedTables &st = *reinterpret_cast<dev::SharedTables *>(s_tex + 36 * kThreads6x6);
+    typename TX::Slot *s_tex = reinterpret_cast<typename TX::Slot *>(smem_raw);         // [kPark6x6][kThreads6x6]
+    dev::SharedTables &st = *reinterpret_cast<dev::SharedTables *>(s_tex + kPark6x6 * kThreads6x6);
     load_shared_tables<ALPHA, SRGB, false>(st);
     __syncthreads();
     const uint32_t s_field = smem_addr(st.field), s_trit = smem_addr(st.trit_scattered);
-    float4 *col = s_tex + threadIdx.x;
 
     // CTA b owns ids [b*BPT*T, (b+1)*BPT*T); a thread re-uses its own shared-memory column for
     // each of its blocks (only it reads or writes that column: no barrier between passes).
@@ -378,15 +418,14 @@ encode6x6_kernel(const EncodeParams p)
 #pragma unroll 1
     for (int pass = 0;; ++pass) {
         f2 sum_lo = dev::bc(0.f), sum_hi = dev::bc(0.f);
+        TX tx;
+        tx.col = s_tex + threadIdx.x;
         const ImageDesc &d = wk.desc(p);
         const uint32_t x0 = wk.bx * 6u, y0 = wk.by * 6u;
         const size_t pitch = d.pitch;
         const uint32_t width = uint32_t(d.width), height = uint32_t(d.height);
         const uint8_t *base = d.rgba + size_t(y0) * pitch + size_t(x0) * 4u;
-        auto park = [&](int k, uint32_t w) {
-            const Texel t = convert_texel<SRGB, NORMAL, false>(w, st.lut_rgb, nullptr, sum_lo, sum_hi);
-            col[k * kThreads6x6] = make_float4(t.lo.x, t.lo.y, t.hi.x, t.hi.y);
-        };
+        auto park = [&](int k, uint32_t w) { tx.put(k, convert_texel<SRGB, NORMAL, false>(w, st.lut_rgb, nullptr, sum_lo, sum_hi)); };
         if ((d.flags & kFlagAligned8) && x0 + 6u <= width && y0 + 6u <= height) {
             // interior: a block row is 24 B = three 8-byte loads; a warp covers 768
             // contiguous bytes per texel row.  All 18 loads are issued before the first use.
@@ -396,10 +435,8 @@ encode6x6_kernel(const EncodeParams p)
                 const uint2 *src = (const uint2 *)(base + size_t(r) * pitch);
                 rows[3 * r + 0] = __ldg(src); rows[3 * r + 1] = __ldg(src + 1); rows[3 * r + 2] = __ldg(src + 2);
             }
-#if ASTC_L2_PREFETCH_6X6
             // The thread's next block: pull its six rows into L2 now, so the loads above hit L2
-            // instead of HBM one pass later (there is no shared memory left for a cp.async stage
-            // and no registers for a software prefetch).
+            // instead of HBM one pass later.
             if (pass + 1 < p.passes) {
                 Walk<BATCH> nx = wk;
                 if (nx.advance(p, kThreads6x6)) {
@@ -412,11 +449,12 @@ encode6x6_kernel(const EncodeParams p)
                     }
                 }
             }
-#endif
 #pragma unroll
             for (int i = 0; i < 18; ++i) { park(2 * i, rows[i].x); park(2 * i + 1, rows[i].y); }
         } else {
-#pragma unroll 6
+            // edge / unaligned: per-texel loads, out-of-range texels read as 0 like Texture2D.Load
+            // (ASTC_Encode.hlsl:574).  Unrolled: the texels kept in registers need constant indices.
+#pragma unroll
             for (int k = 0; k < 36; ++k) {
                 const uint32_t kx = k % 6, ky = k / 6;
                 const bool inside = x0 + kx < width && y0 + ky < height;
@@ -424,16 +462,12 @@ encode6x6_kernel(const EncodeParams p)
             }
         }
         if (NORMAL) sum_hi = dev::bc(36.0f * 255.0f);
-        Texels6x6 tx{col};
+        tx.fence();                                        // no store-to-load forwarding: the passes stream from shared memory
         *wk.out(p) = dev::encode_block<6, ALPHA, NORMAL>(tx, sum_lo, sum_hi, s_field, s_trit);
         if (pass + 1 >= p.passes || !wk.advance(p, kThreads6x6)) break;
     }
 }
 
-#ifndef ASTC_EXTRA_SMEM_6X6
-#define ASTC_EXTRA_SMEM_6X6 0            // occupancy experiments only (tools/variants.py)
-#endif
-constexpr size_t kSmem6x6 = size_t(36) * kThreads6x6 * sizeof(float4) + sizeof(dev::SharedTables) + ASTC_EXTRA_SMEM_6X6;
 
 // ---------------------------------------------------------------------------
 // launch
@@ -467,11 +501,13 @@ static cudaError_t launch_variant(int dim, EncodeParams p, cudaStream_t stream)
         if (ctas > 0x7FFFFFFFull) return cudaErrorInvalidConfiguration;
         encode4x4_kernel<ALPHA, NORMAL, SRGB, BATCH><<<unsigned(ctas), kThreads4x4, 0, stream>>>(p);
     } else {
-        p.passes = choose_passes(p.total_blocks, kThreads6x6, 3, 2);
+        auto kern = encode6x6_kernel<ALPHA, NORMAL, SRGB, BATCH>;
+        constexpr size_t kSmem6x6 = smem6x6<NORMAL>();
+        constexpr int kCtas6x6 = ctas6x6<NORMAL>();
+        p.passes = choose_passes(p.total_blocks, kThreads6x6, kCtas6x6, 2);
         const uint64_t per_cta6 = uint64_t(kThreads6x6) * uint64_t(p.passes);
         const uint64_t ctas = (p.total_blocks + per_cta6 - 1) / per_cta6;
         if (ctas > 0x7FFFFFFFull) return cudaErrorInvalidConfiguration;
-        auto kern = encode6x6_kernel<ALPHA, NORMAL, SRGB, BATCH>;
         static thread_local int configured_device = -1;
         int devno = 0;
         cudaGetDevice(&devno);

@@ -1,5 +1,5 @@
 """Tiny driver for ncu: launches one encode configuration a few times.
-    python tools/profile_target.py 4x4rgb16k|4x4rgb4k|4x4rgba4k|6x6rgba8k|norm4k [iters]"""
+    python tools/profile_target.py 4x4rgb16k|4x4rgb4k|4x4rgba4k|6x6rgba8k|6x6rgb8k|norm4k [iters]"""
 import sys
 import torch
 sys.path.insert(0, ".")
@@ -11,6 +11,7 @@ CFG = {
     "4x4rgb4k": (4096, 4096, synth.SEED_CFG2, A.encode_option(), False),
     "4x4rgba4k": (4096, 4096, synth.SEED_CFG2, A.encode_option(has_alpha=True), False),
     "6x6rgba8k": (8192, 8192, synth.SEED_CFG3, A.encode_option(is6x6=True, has_alpha=True, srgb=True), False),
+    "6x6rgb8k": (8192, 8192, synth.SEED_CFG3, A.encode_option(is6x6=True), False),
     "norm4k": (4096, 4096, synth.SEED_CFG4, A.encode_option(is_normal_map=True), True),
 }
 

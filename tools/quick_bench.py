@@ -28,6 +28,8 @@ if __name__ == "__main__":
         run(4096, 4096, A.encode_option(has_alpha=True), "4x4 rgba")
         run(8192, 8192, A.encode_option(is6x6=True, has_alpha=True, srgb=True), "6x6 rgba srgb")
         run(8192, 8192, A.encode_option(is6x6=True), "6x6 rgb")
+        run(8192, 8192, A.encode_option(is6x6=True, is_normal_map=True), "6x6 norm")
+        run(4096, 4096, A.encode_option(is6x6=True, has_alpha=True), "6x6 rgba 4k")
         run(4096, 4096, A.encode_option(srgb=True), "4x4 rgb srgb")
         run(4096, 4096, A.encode_option(is_normal_map=True), "4x4 norm")
         run(16384, 16384, A.encode_option(is_normal_map=True), "4x4 norm")
