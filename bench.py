@@ -357,6 +357,19 @@ def run_b200(args) -> int:
                                 "kind": "port", "sample": f"block rows 0..{rows_texels // 4 - 1} ({W16K}x{rows_texels} texels) "
                                 "of the same texture, oracle/astc_oracle.c with OpenMP"}
         line["parity"] = {"blocks_checked": int(want.shape[0]), "bit_identical": same}
+        # decoded PSNR (per channel, dB) of the GPU's blocks (device decoder) and of the oracle's blocks
+        # (oracle decoder) against the source, on the first 1024 texel rows of the sample: the metric's
+        # "decoded PSNR delta vs ref" (0 when every block is bit-identical)
+        import numpy as np
+        prow = 1024
+        nblk = (prow // 4) * (W16K // 4)
+        dec_gpu = A.decode_astc(out[:nblk], W16K, prow, 4).cpu().numpy()
+        dec_ref, nbad = O.decode_image(want[:nblk], W16K, prow, 4)
+        src = sample[:prow]
+        p_gpu, p_ref = O.psnr_per_channel(dec_gpu[..., :3], src[..., :3]), O.psnr_per_channel(dec_ref[..., :3], src[..., :3])
+        line["parity"].update({"psnr_db_rgb": [round(float(v), 3) for v in p_gpu],
+                               "psnr_delta_db_vs_oracle": round(float(np.max(np.abs(p_gpu - p_ref))), 4),
+                               "undecodable_blocks": int(nbad)})
 
     # ---- the other BASELINE.json configs, kernel-only, L2 flushed between launches ----
     if world == 1 and not args.no_others:
@@ -390,7 +403,7 @@ def other_configs(torch, A, synth, dev, peak):
     one("4096x4096 normal map, -norm -4x4", synth.synth_normal(4096, 4096, synth.SEED_CFG4, device=dev),
         A.encode_option(is_normal_map=True), 4)
     # batch of 2048x2048 mip chains in one launch over a prefix-summed block table
-    chains = 64
+    chains = 512                                                 # BASELINE config 5: 11.45 GB of texels resident, 178 957 824 blocks
     srcs = []
     for i in range(chains):
         srcs.extend(synth.mip_chain(synth.synth_rgba(2048, 2048, synth.SEED_BATCH + i, device=dev)))
