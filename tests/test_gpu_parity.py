@@ -57,3 +57,51 @@ def test_leaf_alpha_4x4_vs_oracle_and_golden(native, oracle, leaf_rgba, leaf_gol
     assert (got == want).all(), _mismatch_report(got, want)
     same = (got == gold).all(axis=1).mean()
     assert same >= 0.995, f"only {same:.4%} of blocks match the reference's golden leaf.astc"
+
+
+def _mixed_content(rng, w, h):
+    """An image stitched from tiles of different statistics: noise, flat colour, two-colour edges,
+    smooth ramps, saturated extremes, near-flat (+-1) and single-channel variation -- the cases in
+    which the power iteration exits early, the axis is degenerate or the endpoints clamp."""
+    img = np.zeros((h, w, 4), dtype=np.uint8)
+    tile = 12                                             # lcm(4, 6): every tile boundary is a block boundary for both sizes
+    ys, xs = np.mgrid[0:h, 0:w]
+    for ty in range(0, h, tile):
+        for tx in range(0, w, tile):
+            sl = (slice(ty, min(h, ty + tile)), slice(tx, min(w, tx + tile)))
+            shape = img[sl].shape
+            kind = int(rng.integers(0, 8))
+            if kind == 0:
+                t = rng.integers(0, 256, shape)
+            elif kind == 1:
+                t = np.broadcast_to(rng.integers(0, 256, (1, 1, 4)), shape)
+            elif kind == 2:
+                a, b = rng.integers(0, 256, (2, 1, 1, 4))
+                t = np.where(((xs[sl] + ys[sl]) % int(rng.integers(2, 7)) == 0)[..., None], a, b)
+            elif kind == 3:
+                g = rng.integers(-8, 9, (2, 4))
+                t = 128 + xs[sl][..., None] % tile * g[0] + ys[sl][..., None] % tile * g[1]
+            elif kind == 4:
+                t = rng.choice([0, 255], shape)
+            elif kind == 5:
+                t = np.broadcast_to(rng.integers(1, 255, (1, 1, 4)), shape) + rng.integers(-1, 2, shape)
+            elif kind == 6:
+                t = np.broadcast_to(rng.integers(0, 256, (1, 1, 4)), shape).copy()
+                t[..., int(rng.integers(0, 4))] = rng.integers(0, 256, shape[:2])
+            else:
+                t = rng.integers(0, 256, shape) // 64 * 64
+            img[sl] = np.clip(t, 0, 255).astype(np.uint8)
+    return img
+
+
+@pytest.mark.parametrize("dim", [4, 6])
+@pytest.mark.parametrize("seed", range(6))
+def test_mixed_content_all_variants(native, oracle, dim, seed):
+    """Seeded differential run over stitched content classes, ragged sizes and every option set."""
+    rng = np.random.default_rng(4200 + seed)
+    w, h = int(rng.integers(13, 400)), int(rng.integers(13, 300))
+    img = _mixed_content(rng, w, h)
+    for v in VARIANTS:
+        got = _gpu_encode(native, img, _opt(native, dim, v))
+        want = oracle.encode_image(img, block_dim=dim, **v)
+        assert got.shape == want.shape and np.array_equal(got, want), ((w, h), v, _mismatch_report(got, want))
