@@ -67,3 +67,30 @@ def test_full_size_config(native, oracle, name, w, h, dim, kw, kind):
     mse = float(((decf - src) ** 2).mean())
     psnr = 10 * np.log10(255.0 ** 2 / mse)
     assert psnr > (30.0 if kind == "normal" else 22.0), (name, psnr)
+
+
+ALL_VARIANTS = [
+    dict(), dict(has_alpha=True), dict(srgb=True), dict(has_alpha=True, srgb=True),
+    dict(is_normal_map=True), dict(has_alpha=True, is_normal_map=True),
+]
+
+
+@pytest.mark.parametrize("dim", [4, 6])
+@pytest.mark.parametrize("kw", ALL_VARIANTS, ids=lambda k: "-".join(sorted(k)) or "rgb")
+def test_every_variant_whole_image_vs_oracle(native, oracle, dim, kw):
+    """Every option set x both block sizes on a 2050 x 1030 texture (ragged in both directions for 4x4
+    and 6x6; a few hundred CTAs, several blocks per thread): the WHOLE output against the oracle."""
+    import torch
+    from astc_encoder_b200 import synth
+    w, h = 2050, 1030
+    gen = synth.synth_normal if kw.get("is_normal_map") else synth.synth_rgba
+    img = gen(w, h, 0xA57C2000 + dim, device="cuda")
+    opt = native.encode_option(is4x4=dim == 4, is6x6=dim == 6, **kw)
+    got = native.encode_astc(img, opt)
+    torch.cuda.synchronize()
+    okw = dict(has_alpha=bool(kw.get("has_alpha")), is_normal_map=bool(kw.get("is_normal_map")), srgb=bool(kw.get("srgb")))
+    want = oracle.encode_image(img.cpu().numpy(), block_dim=dim, **okw)
+    got = got.cpu().numpy()
+    assert got.shape == want.shape
+    bad = int((got != want).any(axis=1).sum())
+    assert bad == 0, f"{bad} of {len(want)} blocks differ"
