@@ -26,7 +26,7 @@ import numpy as np
 __all__ = [
     "encode_option", "AstcError", "lib", "block_dim", "block_counts", "output_size", "band",
     "encode_astc", "encode_astc_host", "read_gpu", "save_astc", "load_astc", "load_image", "load_tex",
-    "decode_astc", "bise_encode", "Batch", "launch_count", "unorm_lut", "version",
+    "decode_astc", "downsample2x2", "mip_chain", "bise_encode", "Batch", "launch_count", "unorm_lut", "version",
 ]
 
 _PKG = Path(__file__).resolve().parent
@@ -121,6 +121,7 @@ _SIGNATURES = {
     "astc_b200_blockmode": (C.c_uint32, [C.c_int]),
     "astc_b200_unorm_lut": (C.c_int, [C.c_int, C.POINTER(C.c_float)]),
     "astc_b200_decode_device": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "astc_b200_downsample2x2_device": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
     "astc_b200_malloc_device": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "astc_b200_free_device": (C.c_int, [C.c_void_p]),
     "astc_b200_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
@@ -309,6 +310,28 @@ def decode_astc(blocks, width: int, height: int, dim: int, stream=None):
     _check(lib().astc_b200_decode_device(blocks.data_ptr(), width, height, dim, out.data_ptr(), width * 4,
                                          _stream_ptr(stream)), "decode_astc")
     return out
+
+
+def downsample2x2(img, out=None, stream=None):
+    """Next mip level of a CUDA uint8 (H, W, 4) image: 2x2 box filter, round half up -> (max(1,H//2), max(1,W//2), 4)."""
+    import torch
+    if img.dtype != torch.uint8 or img.dim() != 3 or img.shape[2] != 4 or not img.is_cuda or img.stride(2) != 1 or img.stride(1) != 4:
+        raise ValueError("downsample2x2 expects a CUDA uint8 (H, W, 4) tensor with contiguous texels")
+    h, w = int(img.shape[0]), int(img.shape[1])
+    oh, ow = max(1, h // 2), max(1, w // 2)
+    if out is None:
+        out = torch.empty((oh, ow, 4), dtype=torch.uint8, device=img.device)
+    _check(lib().astc_b200_downsample2x2_device(img.data_ptr(), w, h, int(img.stride(0)), out.data_ptr(), int(out.stride(0)),
+                                                _stream_ptr(stream)), "downsample2x2")
+    return out
+
+
+def mip_chain(base, stream=None):
+    """[base, level 1, ..., 1x1] generated on the device, one launch per level."""
+    chain = [base]
+    while chain[-1].shape[0] > 1 or chain[-1].shape[1] > 1:
+        chain.append(downsample2x2(chain[-1], stream=stream))
+    return chain
 
 
 def bise_encode(values, quant: int, stream=None):

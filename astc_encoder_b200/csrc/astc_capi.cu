@@ -402,6 +402,21 @@ int astc_b200_decode_device(const uint8_t *d_blocks, int width, int height, int 
     return ASTC_B200_OK;
 }
 
+int astc_b200_downsample2x2_device(const uint8_t *d_src, int width, int height, size_t src_pitch_bytes, uint8_t *d_dst,
+                                   size_t dst_pitch_bytes, void *cuda_stream)
+{
+    if (width < 0 || height < 0) return ASTC_B200_ERR_INVALID_ARGUMENT;
+    if (width == 0 || height == 0) return ASTC_B200_OK;
+    const size_t ow = width > 1 ? size_t(width) / 2u : 1u;
+    if (!d_src || !d_dst || src_pitch_bytes < size_t(width) * 4u || dst_pitch_bytes < ow * 4u || src_pitch_bytes % 4u != 0 ||
+        dst_pitch_bytes % 4u != 0 || reinterpret_cast<uintptr_t>(d_src) % 4u != 0 || reinterpret_cast<uintptr_t>(d_dst) % 4u != 0)
+        return ASTC_B200_ERR_INVALID_ARGUMENT;
+    CUDA_TRY(astc::launch_downsample2x2(d_src, width, height, src_pitch_bytes, d_dst, dst_pitch_bytes,
+                                        static_cast<cudaStream_t>(cuda_stream)));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return ASTC_B200_OK;
+}
+
 int astc_b200_malloc_device(void **d_ptr, size_t bytes)
 {
     if (!d_ptr) return ASTC_B200_ERR_INVALID_ARGUMENT;

@@ -702,4 +702,81 @@ cudaError_t launch_decode(const uint8_t *d_blocks, int width, int height, int di
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------
+// 2x2 box-filter downsample of an RGBA8 image: the next level of a mip chain, produced on the
+// device for the batch configuration (the reference has no mip generation, its
+// caller would upload each level).  out(x, y) = (sum of the 2x2 source texels + 2) >> 2 per
+// channel (round half up); an odd trailing row / column is dropped, a dimension of 1 stays 1.
+// HBM-bound: 4 bytes read + 1 written per source texel.  Fast path: a thread makes four output
+// texels from two rows of eight -- four 16-byte loads and one 16-byte store, a warp reads 2 x 1 KB
+// and writes 512 B, all contiguous.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t box4(uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    constexpr uint32_t M = 0x00FF00FFu, R = 0x00020002u;      // two channels per word in 16-bit lanes
+    const uint32_t rb = (a & M) + (b & M) + (c & M) + (d & M) + R;
+    const uint32_t ga = ((a >> 8) & M) + ((b >> 8) & M) + ((c >> 8) & M) + ((d >> 8) & M) + R;
+    return ((rb >> 2) & M) | (((ga >> 2) & M) << 8);
+}
+
+__global__ void __launch_bounds__(256)
+downsample2x2_vec_kernel(const uint8_t *__restrict__ src, size_t src_pitch, uint8_t *__restrict__ dst, size_t dst_pitch,
+                         uint32_t quads_x, uint64_t total_quads)
+{
+    for (uint64_t q = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; q < total_quads; q += uint64_t(gridDim.x) * blockDim.x) {
+        const uint32_t y = uint32_t(q / quads_x), xq = uint32_t(q - uint64_t(y) * quads_x);
+        const uint4 *r0 = reinterpret_cast<const uint4 *>(src + size_t(2u * y) * src_pitch) + 2u * xq;
+        const uint4 *r1 = reinterpret_cast<const uint4 *>(src + size_t(2u * y + 1u) * src_pitch) + 2u * xq;
+        const uint4 a0 = __ldcs(r0), a1 = __ldcs(r0 + 1), b0 = __ldcs(r1), b1 = __ldcs(r1 + 1);   // streamed: read once
+        uint4 o;
+        o.x = box4(a0.x, a0.y, b0.x, b0.y);
+        o.y = box4(a0.z, a0.w, b0.z, b0.w);
+        o.z = box4(a1.x, a1.y, b1.x, b1.y);
+        o.w = box4(a1.z, a1.w, b1.z, b1.w);
+        reinterpret_cast<uint4 *>(dst + size_t(y) * dst_pitch)[xq] = o;
+    }
+}
+
+// any size / alignment: one thread per output texel
+__global__ void __launch_bounds__(256)
+downsample2x2_scalar_kernel(const uint8_t *__restrict__ src, size_t src_pitch, int width, int height, uint8_t *__restrict__ dst,
+                            size_t dst_pitch, uint32_t out_w, uint64_t total)
+{
+    const uint32_t dx = width > 1 ? 1u : 0u, dy = height > 1 ? 1u : 0u;
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += uint64_t(gridDim.x) * blockDim.x) {
+        const uint32_t y = uint32_t(i / out_w), x = uint32_t(i - uint64_t(y) * out_w);
+        const uint8_t *p0 = src + size_t(y << dy) * src_pitch + size_t(x << dx) * 4u;
+        const uint8_t *p1 = p0 + size_t(dy) * src_pitch;
+        const uint32_t a = *reinterpret_cast<const uint32_t *>(p0), b = *reinterpret_cast<const uint32_t *>(p0 + 4u * dx);
+        const uint32_t c = *reinterpret_cast<const uint32_t *>(p1), d = *reinterpret_cast<const uint32_t *>(p1 + 4u * dx);
+        *reinterpret_cast<uint32_t *>(dst + size_t(y) * dst_pitch + size_t(x) * 4u) = box4(a, b, c, d);
+    }
+}
+
+cudaError_t launch_downsample2x2(const uint8_t *d_src, int width, int height, size_t src_pitch, uint8_t *d_dst, size_t dst_pitch,
+                                 cudaStream_t stream)
+{
+    const uint32_t ow = uint32_t(width > 1 ? width / 2 : 1), oh = uint32_t(height > 1 ? height / 2 : 1);
+    static thread_local int sm_count = 0;
+    if (sm_count == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+            sm_count = 148;
+    }
+    const uint64_t max_ctas = uint64_t(sm_count) * 8u * 4u;                   // 8 resident CTAs of 256 threads per SM, four waves
+    const bool vec = width > 1 && height > 1 && ow % 4u == 0 && src_pitch % 16u == 0 && dst_pitch % 16u == 0 &&
+                     reinterpret_cast<uintptr_t>(d_src) % 16u == 0 && reinterpret_cast<uintptr_t>(d_dst) % 16u == 0;
+    if (vec) {
+        const uint64_t total = uint64_t(ow / 4u) * oh;
+        const uint64_t ctas = (total + 255) / 256;
+        downsample2x2_vec_kernel<<<unsigned(ctas < max_ctas ? ctas : max_ctas), 256, 0, stream>>>(d_src, src_pitch, d_dst, dst_pitch, ow / 4u, total);
+    } else {
+        const uint64_t total = uint64_t(ow) * oh;
+        const uint64_t ctas = (total + 255) / 256;
+        downsample2x2_scalar_kernel<<<unsigned(ctas < max_ctas ? ctas : max_ctas), 256, 0, stream>>>(d_src, src_pitch, width, height, d_dst,
+                                                                                                   dst_pitch, ow, total);
+    }
+    return cudaGetLastError();
+}
+
 }  // namespace astc

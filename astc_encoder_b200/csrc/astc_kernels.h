@@ -36,6 +36,8 @@ cudaError_t launch_encode(int dim, bool alpha, bool normal, bool srgb, const Enc
 cudaError_t launch_bise(const uint8_t *d_values, int count, int quant, int nseq, uint8_t *d_streams, cudaStream_t stream);
 cudaError_t launch_decode(const uint8_t *d_blocks, int width, int height, int dim, uint8_t *d_rgba, size_t pitch,
                           cudaStream_t stream);
+cudaError_t launch_downsample2x2(const uint8_t *d_src, int width, int height, size_t src_pitch, uint8_t *d_dst, size_t dst_pitch,
+                                 cudaStream_t stream);
 const float *host_srgb_lut();
 const float *host_unorm_lut();   // the c / 255.0f table the 4x4 kernels look up
 

@@ -406,7 +406,7 @@ def other_configs(torch, A, synth, dev, peak):
     chains = 512                                                 # BASELINE config 5: 11.45 GB of texels resident, 178 957 824 blocks
     srcs = []
     for i in range(chains):
-        srcs.extend(synth.mip_chain(synth.synth_rgba(2048, 2048, synth.SEED_BATCH + i, device=dev)))
+        srcs.extend(A.mip_chain(synth.synth_rgba(2048, 2048, synth.SEED_BATCH + i, device=dev)))   # device 2x2 box filter
     batch = A.Batch(srcs, A.encode_option())
     ms = _time_launches(torch, lambda: batch.encode(), 10, 3, None)
     res.append({"workload": f"{chains} x 2048x2048 12-level mip chains, 4x4 RGB, ONE launch", "value": round(batch.total_texels / ms / 1e3, 1),

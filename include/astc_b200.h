@@ -151,6 +151,16 @@ ASTC_B200_API int astc_b200_decode_device(const uint8_t *d_blocks, int width, in
                                           int block_dim, uint8_t *d_rgba, size_t pitch_bytes,
                                           void *cuda_stream);
 
+/* ---- mip generation on the device (not in the reference, whose caller -----
+ *      main.cpp:19-56 load_tex -- uploads one level) ---------------------------------------- */
+/* Next mip level of an RGBA8 image by 2x2 box filter, (sum + 2) >> 2 per channel; output is
+ * max(1, width/2) x max(1, height/2) (an odd trailing row / column is dropped). Async on the
+ * stream; device pointers, 4-byte aligned (16-byte alignment of bases and pitches and an output
+ * width that is a multiple of 4 take the vector path). */
+ASTC_B200_API int astc_b200_downsample2x2_device(const uint8_t *d_src, int width, int height,
+                                                 size_t src_pitch_bytes, uint8_t *d_dst,
+                                                 size_t dst_pitch_bytes, void *cuda_stream);
+
 /* ---- memory / streams (so hosts need not link the CUDA runtime) -------- */
 ASTC_B200_API int astc_b200_malloc_device(void **d_ptr, size_t bytes);
 ASTC_B200_API int astc_b200_free_device(void *d_ptr);

@@ -182,3 +182,16 @@ def psnr_per_channel(a: np.ndarray, b: np.ndarray) -> np.ndarray:
     mse = (d * d).reshape(-1, a.shape[-1]).mean(axis=0)
     with np.errstate(divide="ignore"):
         return 10.0 * np.log10(255.0 * 255.0 / mse)
+
+
+def downsample2x2(img: np.ndarray) -> np.ndarray:
+    """Checker for astc_b200_downsample2x2_device (not part of the reference: SURVEY.md 8f N3).
+    2x2 box filter on (H, W, 4) uint8, (sum + 2) >> 2; odd trailing row / column dropped; a
+    dimension of 1 stays 1 (its texel counted twice)."""
+    h, w = img.shape[0], img.shape[1]
+    oh, ow = max(1, h // 2), max(1, w // 2)
+    c = img.astype(np.uint32)
+    ys = (np.arange(oh) * 2, np.arange(oh) * 2 + 1) if h > 1 else (np.zeros(1, int), np.zeros(1, int))
+    xs = (np.arange(ow) * 2, np.arange(ow) * 2 + 1) if w > 1 else (np.zeros(1, int), np.zeros(1, int))
+    acc = sum(c[np.ix_(ys[j], xs[i])] for j in range(2) for i in range(2))
+    return ((acc + 2) >> 2).astype(np.uint8)

@@ -72,4 +72,7 @@ def test_argument_validation(native):
     assert L.astc_b200_encode_host(None, 16, 16, 64, C.byref(o), None) == -1
     assert L.astc_b200_encode_host(None, 0, 16, 0, C.byref(o), None) == 0
     assert L.astc_b200_decode_device(None, 4, 4, 5, None, 16, None) == -1
+    assert L.astc_b200_downsample2x2_device(None, 8, 8, 32, None, 16, None) == -1      # null pointers
+    assert L.astc_b200_downsample2x2_device(None, -1, 8, 32, None, 16, None) == -1
+    assert L.astc_b200_downsample2x2_device(None, 0, 8, 32, None, 16, None) == 0       # empty image: nothing to do
     assert L.astc_b200_bise_encode_device(None, 65, 0, 1, None, None) == -1

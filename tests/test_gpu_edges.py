@@ -194,3 +194,25 @@ def test_batch_walk_over_many_tiny_images(native, oracle, dim, passes, monkeypat
         want = oracle.encode_image(img, **_okw(opt, dim))
         assert np.array_equal(o.cpu().numpy(), want), img.shape
     batch.close()
+
+
+@pytest.mark.parametrize("size", [(2048, 2048), (64, 32), (8, 8), (250, 187), (7, 5), (2, 2), (1, 9), (9, 1), (1, 1), (33, 2), (4099, 3)], ids=str)
+def test_device_mip_downsample(native, oracle, size):
+    """astc_b200_downsample2x2_device (vector and scalar paths, degenerate sizes) against the numpy
+    restatement, and the device-built chain against torch's (astc_encoder_b200.synth.mip_chain)."""
+    import torch
+    from astc_encoder_b200 import synth
+    w, h = size
+    rng = np.random.default_rng(w * 131 + h)
+    img = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+    d = torch.from_numpy(img).cuda()
+    got = native.downsample2x2(d)
+    torch.cuda.synchronize()
+    assert np.array_equal(got.cpu().numpy(), oracle.downsample2x2(img))
+    chain = native.mip_chain(d)
+    ref = synth.mip_chain(d)
+    assert len(chain) == len(ref) and all(torch.equal(a, b) for a, b in zip(chain, ref))
+    # a strided (pitched) view takes the scalar or the vector path depending on alignment
+    wide = torch.zeros((h, w + 3, 4), dtype=torch.uint8, device="cuda")
+    wide[:, 1:w + 1] = d
+    assert torch.equal(native.downsample2x2(wide[:, 1:w + 1]), got)
