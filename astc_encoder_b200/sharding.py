@@ -115,3 +115,44 @@ def gather_blocks(local: np.ndarray, width: int, height: int, option: encode_opt
     for p, t in zip(plan, parts):
         out[p.byte_offset:p.byte_offset + p.nbytes] = t[: p.nbytes].cpu().numpy()
     return out.reshape(-1, BLOCK_BYTES)
+
+
+def _parse_cpulist(text: str) -> set:
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_host_to_gpu(device_index: int) -> dict:
+    """One process per GPU: restrict this process to the CPUs of the GPU's NUMA node, so that the
+    pinned staging buffers it allocates afterwards are placed (first touch) in the memory next to
+    the GPU's PCIe root port.  With eight ranks each streaming > 1 GiB per call through
+    astc_b200_encode_host, buffers on the wrong socket cross the inter-socket link and the
+    end-to-end rate collapses.  Returns what was done; never raises (a container may forbid it)."""
+    import os
+    info = {"bound": False}
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = f"{getattr(p, 'pci_domain_id', 0):04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        info["pci"] = bdf
+        base = f"/sys/bus/pci/devices/{bdf}"
+        with open(f"{base}/local_cpulist") as f:
+            local = _parse_cpulist(f.read())
+        try:
+            with open(f"{base}/numa_node") as f:
+                info["numa_node"] = int(f.read())
+        except OSError:
+            pass
+        allowed = os.sched_getaffinity(0) & local
+        if allowed and allowed != os.sched_getaffinity(0):
+            os.sched_setaffinity(0, allowed)
+            info["bound"] = True
+        info["cpus"] = len(os.sched_getaffinity(0))
+    except Exception as e:                                   # noqa: BLE001
+        info["error"] = repr(e)
+    return info

@@ -212,9 +212,25 @@ def run_b200(args) -> int:
         raise SystemExit("bench.py needs a CUDA device: the encoder has no CPU path (use --impl reference for the CPU oracle)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = None
+    if world > 1 and not os.environ.get("ASTC_BENCH_NO_NUMA"):
+        from astc_encoder_b200 import sharding
+        numa = sharding.bind_host_to_gpu(local)                  # before the pinned buffers are allocated
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL writes its "NCCL version ..." banner to STDOUT when the first communicator comes up;
+        # stdout is reserved for the one JSON line, so fd 1 points at stderr until that has happened.
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     A.lib()
 
     def barrier():
@@ -329,7 +345,7 @@ def run_b200(args) -> int:
                 "d2h_bytes_per_step": texels, "steps": e2e_steps, "ms_per_step": round(e2e_s * 1e3, 3),
                 "api": "astc_b200_encode_host (C ABI), pinned host buffers", "launches": int(e2e_launches),
                 "matches_device_path": e2e_identical,
-                "link_only_ms": round(link_ms, 3),
+                "link_only_ms": round(link_ms, 3), "host_numa_binding": numa,
                 "note": "PCIe-bound: link_only_ms is the same H2D + D2H traffic with no kernel at all"},
         "gpu_launches": int(launches),
         "clocks": clocks,
