@@ -118,3 +118,11 @@ def test_gpu_bands_concatenate_to_full_encode(native, dim, parts):
     full = native.read_gpu(native.encode_astc(img.cuda(), opt))
     got = np.concatenate([sharding.encode_band(img.numpy(), opt, r, parts)[1] for r in range(parts)])
     assert np.array_equal(got, full)
+
+
+def test_cpulist_parser_and_numa_binding_never_raises():
+    from astc_encoder_b200 import sharding
+    assert sharding._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert sharding._parse_cpulist("") == set()
+    info = sharding.bind_host_to_gpu(0)          # no GPU here: reports the error instead of raising
+    assert isinstance(info, dict) and "bound" in info
