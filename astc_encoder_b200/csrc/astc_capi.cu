@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -218,8 +219,19 @@ int astc_b200_encode_host(const uint8_t *h_rgba, int width, int height, size_t p
     const int d = dim_of(opt);
     const int64_t bx = (width + d - 1) / d, by = (height + d - 1) / d;
     const size_t d_pitch = (size_t(width) * 4u + 127u) & ~size_t(127);
-    // bands of ~8 MiB of source keep the three engines (H2D, SM, D2H) busy at once
-    const int64_t rows_per_band = std::max<int64_t>(1, (int64_t(8) << 20) / int64_t(d_pitch * size_t(d)));
+    // Bands keep the three engines (H2D, SM, D2H) busy at once.  The H2D copies are the bottleneck and
+    // run back to back; what the banding costs on top is the drain after the last copy (that band's
+    // kernel and its D2H: ~5.2 ps per byte of band) plus ~7.8 us of launch / copy overhead per band
+    // (both measured on B200 / PCIe Gen5: 1 GiB in 1 / 8 / 32 / 128 MiB bands = 28.4 / 20.8 / 20.45 /
+    // 20.9 ms).  The sum is smallest at sqrt(5.2e-12 / 7.8e-6 * bytes) bands: 27 for 1 GiB, 7 for 64 MiB.
+    // ASTC_B200_HOST_BAND_MIB overrides (tuning hook, tools/e2e_sweep.py).
+    const double src_bytes = double(d_pitch) * double(height);
+    int64_t want_bands = std::max<int64_t>(1, int64_t(std::sqrt(6.7e-7 * src_bytes) + 0.5));
+    if (const char *env = getenv("ASTC_B200_HOST_BAND_MIB")) {
+        const long v = atol(env);
+        if (v >= 1 && v <= 1024) want_bands = std::max<int64_t>(1, int64_t(src_bytes / (double(v) * 1048576.0) + 0.5));
+    }
+    const int64_t rows_per_band = std::max<int64_t>(1, (by + want_bands - 1) / want_bands);
     const int nbands = int((by + rows_per_band - 1) / rows_per_band);
     constexpr int kStreams = 3;
     cudaStream_t streams[kStreams] = {};
