@@ -26,7 +26,7 @@ import numpy as np
 __all__ = [
     "encode_option", "AstcError", "lib", "block_dim", "block_counts", "output_size", "band",
     "encode_astc", "encode_astc_host", "read_gpu", "save_astc", "load_astc", "load_image", "load_tex",
-    "decode_astc", "downsample2x2", "mip_chain", "bise_encode", "Batch", "launch_count", "unorm_lut", "version",
+    "decode_astc", "downsample2x2", "mip_chain", "mufu", "bise_encode", "Batch", "launch_count", "unorm_lut", "version",
 ]
 
 _PKG = Path(__file__).resolve().parent
@@ -121,6 +121,7 @@ _SIGNATURES = {
     "astc_b200_blockmode": (C.c_uint32, [C.c_int]),
     "astc_b200_unorm_lut": (C.c_int, [C.c_int, C.POINTER(C.c_float)]),
     "astc_b200_decode_device": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "astc_b200_mufu_device": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "astc_b200_downsample2x2_device": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
     "astc_b200_malloc_device": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "astc_b200_free_device": (C.c_int, [C.c_void_p]),
@@ -332,6 +333,15 @@ def mip_chain(base, stream=None):
     while chain[-1].shape[0] > 1 or chain[-1].shape[1] > 1:
         chain.append(downsample2x2(chain[-1], stream=stream))
     return chain
+
+
+def mufu(op: str, x, stream=None):
+    """rcp.approx.ftz / rsqrt.approx.ftz of a CUDA float32 tensor (op = "rcp" | "rsq")."""
+    import torch
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    _check(lib().astc_b200_mufu_device({"rcp": 0, "rsq": 1}[op], x.data_ptr(), y.data_ptr(), x.numel(), _stream_ptr(stream)), "mufu")
+    return y
 
 
 def bise_encode(values, quant: int, stream=None):

@@ -429,6 +429,16 @@ int astc_b200_downsample2x2_device(const uint8_t *d_src, int width, int height, 
     return ASTC_B200_OK;
 }
 
+int astc_b200_mufu_device(int op, const float *d_x, float *d_y, size_t count, void *cuda_stream)
+{
+    if (op != 0 && op != 1) return ASTC_B200_ERR_INVALID_ARGUMENT;
+    if (count == 0) return ASTC_B200_OK;
+    if (!d_x || !d_y) return ASTC_B200_ERR_INVALID_ARGUMENT;
+    CUDA_TRY(astc::launch_mufu(op, d_x, d_y, count, static_cast<cudaStream_t>(cuda_stream)));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return ASTC_B200_OK;
+}
+
 int astc_b200_malloc_device(void **d_ptr, size_t bytes)
 {
     if (!d_ptr) return ASTC_B200_ERR_INVALID_ARGUMENT;

@@ -779,4 +779,27 @@ cudaError_t launch_downsample2x2(const uint8_t *d_src, int width, int height, si
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------
+// The two hardware approximations the encoder's arithmetic is defined on (MUFU.RCP, MUFU.RSQ),
+// applied to an array: lets tests and tools/gen_mufu_tables.py compare the oracle's table-driven
+// emulation with the device, value by value.
+// ---------------------------------------------------------------------------
+__global__ void mufu_kernel(int op, const float *__restrict__ x, float *__restrict__ y, size_t n)
+{
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+        float r;
+        if (op == 0) asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x[i]));
+        else asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x[i]));
+        y[i] = r;
+    }
+}
+
+cudaError_t launch_mufu(int op, const float *d_x, float *d_y, size_t n, cudaStream_t stream)
+{
+    if (n == 0) return cudaSuccess;
+    const size_t ctas = (n + 255) / 256;
+    mufu_kernel<<<unsigned(ctas < 148u * 32u ? ctas : 148u * 32u), 256, 0, stream>>>(op, d_x, d_y, n);
+    return cudaGetLastError();
+}
+
 }  // namespace astc

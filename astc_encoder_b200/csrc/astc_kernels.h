@@ -38,6 +38,7 @@ cudaError_t launch_decode(const uint8_t *d_blocks, int width, int height, int di
                           cudaStream_t stream);
 cudaError_t launch_downsample2x2(const uint8_t *d_src, int width, int height, size_t src_pitch, uint8_t *d_dst, size_t dst_pitch,
                                  cudaStream_t stream);
+cudaError_t launch_mufu(int op, const float *d_x, float *d_y, size_t n, cudaStream_t stream);
 const float *host_srgb_lut();
 const float *host_unorm_lut();   // the c / 255.0f table the 4x4 kernels look up
 

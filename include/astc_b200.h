@@ -161,6 +161,13 @@ ASTC_B200_API int astc_b200_downsample2x2_device(const uint8_t *d_src, int width
                                                  size_t src_pitch_bytes, uint8_t *d_dst,
                                                  size_t dst_pitch_bytes, void *cuda_stream);
 
+/* ---- the hardware approximations the arithmetic is defined on ------------------------------ */
+/* y[i] = rcp.approx.ftz.f32(x[i]) (op 0) or rsqrt.approx.ftz.f32(x[i]) (op 1): what the reference's
+ * `1.0f / x` (ASTC_Encode.hlsl:366) and normalize() (:103,332) execute on the hardware its golden
+ * output came from. For tests and for generating the oracle's tables. */
+ASTC_B200_API int astc_b200_mufu_device(int op, const float *d_x, float *d_y, size_t count,
+                                        void *cuda_stream);
+
 /* ---- memory / streams (so hosts need not link the CUDA runtime) -------- */
 ASTC_B200_API int astc_b200_malloc_device(void **d_ptr, size_t bytes);
 ASTC_B200_API int astc_b200_free_device(void *d_ptr);

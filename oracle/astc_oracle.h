@@ -27,8 +27,11 @@
  *
  * Canonical float arithmetic (frozen; the CUDA kernel reproduces it bit for
  * bit): IEEE binary32, round-to-nearest-even, explicit fmaf() exactly where
- * written, no other contraction (compile with -ffp-contract=off), correctly
- * rounded sqrtf and division, rintf for HLSL round().
+ * written, no other contraction (compile with -ffp-contract=off), rintf for HLSL
+ * round(); the reciprocal (ASTC_Encode.hlsl:366) and the reciprocal square root
+ * of normalize() (:103,332) are NVIDIA's MUFU.RCP / MUFU.RSQ approximations,
+ * emulated exactly from tables captured on the device (astc_oracle_set_mufu_tables,
+ * oracle/tables/, tools/gen_mufu_tables.py) -- the arithmetic the golden shows.
  */
 #ifndef ASTC_ORACLE_H
 #define ASTC_ORACLE_H
@@ -39,6 +42,12 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+
+/* Delta tables of the MUFU emulation (int8: 2^23 entries for rcp, 2^24 for rsq); must be set
+ * before any encode call -- without them the encoders produce NaN poison, never a fallback. */
+void astc_oracle_set_mufu_tables(const int8_t *rcp_delta, const int8_t *rsq_delta);
+float astc_oracle_mufu_rcp(float x);
+float astc_oracle_mufu_rsq(float x);
 
 /* Mirrors encode_option (astc_encode.h:14-28) after CLI resolution. */
 typedef struct astc_oracle_opt {

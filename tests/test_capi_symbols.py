@@ -72,6 +72,8 @@ def test_argument_validation(native):
     assert L.astc_b200_encode_host(None, 16, 16, 64, C.byref(o), None) == -1
     assert L.astc_b200_encode_host(None, 0, 16, 0, C.byref(o), None) == 0
     assert L.astc_b200_decode_device(None, 4, 4, 5, None, 16, None) == -1
+    assert L.astc_b200_mufu_device(2, None, None, 4, None) == -1                       # unknown op
+    assert L.astc_b200_mufu_device(0, None, None, 4, None) == -1 and L.astc_b200_mufu_device(1, None, None, 0, None) == 0
     assert L.astc_b200_downsample2x2_device(None, 8, 8, 32, None, 16, None) == -1      # null pointers
     assert L.astc_b200_downsample2x2_device(None, -1, 8, 32, None, 16, None) == -1
     assert L.astc_b200_downsample2x2_device(None, 0, 8, 32, None, 16, None) == 0       # empty image: nothing to do

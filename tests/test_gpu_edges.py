@@ -216,3 +216,22 @@ def test_device_mip_downsample(native, oracle, size):
     wide = torch.zeros((h, w + 3, 4), dtype=torch.uint8, device="cuda")
     wide[:, 1:w + 1] = d
     assert torch.equal(native.downsample2x2(wide[:, 1:w + 1]), got)
+
+
+def test_oracle_mufu_emulation_matches_the_device(native, oracle):
+    """rcp.approx.ftz / rsqrt.approx.ftz on this GPU against the oracle's table emulation: random
+    inputs over the range the encoder uses and over the whole normal range, a full sweep of the
+    top 16 mantissa bits for both exponent parities, and the neighbourhood of the powers of two."""
+    import torch
+    rng = np.random.default_rng(11)
+    parts = [np.exp(rng.uniform(np.log(1e-20), np.log(1e22), 1 << 20)).astype(np.float32),
+             rng.integers(0x00800000, 0x7F000000, 1 << 20, dtype=np.uint32).view(np.float32),
+             (np.uint32(0x3F800000) + (np.arange(1 << 17, dtype=np.uint32) << 7)).view(np.float32),
+             (np.uint32(0x3F800000 - 64) + np.arange(128, dtype=np.uint32)).view(np.float32)]
+    x = np.concatenate(parts)
+    d = torch.from_numpy(x).cuda()
+    got_rsq = native.mufu("rsq", d).cpu().numpy()
+    assert np.array_equal(got_rsq.view(np.uint32), oracle.mufu_rsq(x).view(np.uint32))
+    ok = (x > 2.0 ** -125) & (x < 2.0 ** 125)                 # reciprocals that stay normal (ftz beyond)
+    got_rcp = native.mufu("rcp", d).cpu().numpy()
+    assert np.array_equal(got_rcp.view(np.uint32)[ok], oracle.mufu_rcp(x).view(np.uint32)[ok])
