@@ -56,7 +56,7 @@ def test_leaf_alpha_4x4_vs_oracle_and_golden(native, oracle, leaf_rgba, leaf_gol
     want = oracle.encode_image(leaf_rgba, block_dim=4, has_alpha=True)
     assert (got == want).all(), _mismatch_report(got, want)
     same = (got == gold).all(axis=1).mean()
-    assert same >= 0.995, f"only {same:.4%} of blocks match the reference's golden leaf.astc"
+    assert same >= 0.999, f"only {same:.4%} of blocks match the reference's golden leaf.astc"      # north_star: 99.9 %; measured 99.940 %
 
 
 def _mixed_content(rng, w, h):

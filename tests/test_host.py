@@ -152,7 +152,7 @@ def test_cli_reproduces_readme_example(native, oracle, tmp_path, leaf_golden):
     assert (xd, yd, xs, ys) == (4, 4, 1024, 1024)
     want = oracle.encode_image(native.load_image(str(src), True), block_dim=4, has_alpha=True)
     assert np.array_equal(blocks, want)
-    assert (blocks == leaf_golden[4]).all(axis=1).mean() >= 0.995
+    assert (blocks == leaf_golden[4]).all(axis=1).mean() >= 0.999
     # -6x6 -srgb on the same file: header says 6x6, blocks match the oracle
     r = subprocess.run([str(CLI), str(src), "-6x6", "-srgb"], capture_output=True, text=True)
     assert r.returncode == 0 and "is 4x4 block\tfalse" in r.stdout
