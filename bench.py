@@ -354,7 +354,7 @@ def run_b200(args) -> int:
                      "kernel": "encode4x4_kernel<rgb,linear>", "kernel_ms": round(kernel_ms, 4),
                      "kernel_ms_best": round(per[0], 4), "algorithmic_bytes_per_launch": int(texels * BYTES_PER_TEXEL_4x4),
                      "peak_source": peak_src, "compute": compute,
-                     "note": "FP32-pipe / register-operand-bandwidth bound (1137 warp-instructions per 32 blocks of 80 B): DESIGN.md 4.1"},
+                     "note": "FP32-pipe / register-operand-bandwidth bound (~1050 warp-instructions per 32 blocks of 80 B): DESIGN.md 4.1"},
     }
 
     # ---- CPU baseline + parity on a bounded sample of the same texture (rank 0, N=1) ----
