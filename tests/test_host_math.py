@@ -64,14 +64,15 @@ def test_small_length_threshold():
     assert np.array_equal(np.sqrt(xs) < small, xs < k)
 
 
-def test_weight_clamp_never_acts():
-    """x * RN(1/x) <= 1 + 2^-23, so round(w * range) <= range and the reference's clamp is dead code."""
+def test_weight_clamp_never_acts(oracle):
+    """x * rcp(x) <= 1 + 3 * 2^-23 with the MUFU reciprocal (good to 1 ulp), so round(w * range) <= range:
+    the reference's clamp is dead code and the kernel's table index stays in its row."""
     rng = np.random.default_rng(2)
     x = np.concatenate([rng.uniform(1e-5, 1500, 500000), [1e-5, 255.0, 441.67294]]).astype(np.float32)
-    n = (x * (f32(1.0) / x)).astype(np.float32)
-    assert n.max() <= np.nextafter(f32(1.0), f32(2.0))
+    n = (x * oracle.mufu_rcp(x)).astype(np.float32)
+    assert n.max() <= f32(1.0) + f32(3 * 2.0 ** -23) and n.min() >= f32(1.0) - f32(3 * 2.0 ** -23)
     for r in (f32(5.0), f32(11.0)):
-        assert np.rint(n * r).max() == r
+        assert np.rint((n * r).astype(np.float32)).max() == r
 
 
 def test_field_table_reconstructs_trit_packing(oracle):
