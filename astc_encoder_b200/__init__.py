@@ -25,7 +25,7 @@ import numpy as np
 
 __all__ = [
     "encode_option", "AstcError", "lib", "block_dim", "block_counts", "output_size", "band",
-    "encode_astc", "encode_astc_host", "read_gpu", "save_astc", "load_astc", "load_image", "load_tex",
+    "encode_astc", "encode_astc_host", "read_gpu", "save_astc", "save_astc_slice", "load_astc", "load_image", "load_tex",
     "decode_astc", "downsample2x2", "mip_chain", "mufu", "bise_encode", "Batch", "launch_count", "unorm_lut", "version",
 ]
 
@@ -134,6 +134,7 @@ _SIGNATURES = {
     "astc_b200_stream_destroy": (C.c_int, [C.c_void_p]),
     "astc_b200_stream_synchronize": (C.c_int, [C.c_void_p]),
     "astc_b200_save_astc": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
+    "astc_b200_save_astc_slice": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int]),
     "astc_b200_load_astc": (C.c_int, [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                       C.POINTER(C.c_int), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "astc_b200_load_image": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
@@ -367,6 +368,14 @@ def save_astc(astc_path: str, xdim: int, ydim: int, xsize: int, ysize: int, buff
     buf = np.ascontiguousarray(np.asarray(buffer, dtype=np.uint8))
     _check(lib().astc_b200_save_astc(str(astc_path).encode(), xdim, ydim, xsize, ysize, buf.ctypes.data, buf.size),
            "save_astc")
+
+
+def save_astc_slice(astc_path: str, xdim: int, ydim: int, xsize: int, ysize: int, byte_offset: int, buffer,
+                    write_header: bool) -> None:
+    """One rank's slice of a shared .astc file (astc_b200_save_astc_slice): safe in any order, never truncates."""
+    buf = np.ascontiguousarray(np.asarray(buffer, dtype=np.uint8))
+    _check(lib().astc_b200_save_astc_slice(str(astc_path).encode(), xdim, ydim, xsize, ysize, byte_offset,
+                                           buf.ctypes.data, buf.size, int(bool(write_header))), "save_astc_slice")
 
 
 def load_astc(astc_path: str) -> tuple[int, int, int, int, np.ndarray]:

@@ -8,6 +8,9 @@
 #include "astc_b200.h"
 
 #include <cuda_runtime.h>
+#include <fcntl.h>
+#include <sys/types.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
@@ -224,13 +227,15 @@ int astc_b200_encode_host(const uint8_t *h_rgba, int width, int height, size_t p
     // kernel and its D2H: ~5.2 ps per byte of band) plus ~7.8 us of launch / copy overhead per band
     // (both measured on B200 / PCIe Gen5: 1 GiB in 1 / 8 / 32 / 128 MiB bands = 28.4 / 20.8 / 20.45 /
     // 20.9 ms).  The sum is smallest at sqrt(5.2e-12 / 7.8e-6 * bytes) bands: 27 for 1 GiB, 7 for 64 MiB.
-    // ASTC_B200_HOST_BAND_MIB overrides (tuning hook, tools/e2e_sweep.py).
+    // Experiment builds (-DASTC_TUNING_HOOKS) let ASTC_B200_HOST_BAND_MIB override it (tools/e2e_sweep.py).
     const double src_bytes = double(d_pitch) * double(height);
     int64_t want_bands = std::max<int64_t>(1, int64_t(std::sqrt(6.7e-7 * src_bytes) + 0.5));
+#ifdef ASTC_TUNING_HOOKS
     if (const char *env = getenv("ASTC_B200_HOST_BAND_MIB")) {
         const long v = atol(env);
         if (v >= 1 && v <= 1024) want_bands = std::max<int64_t>(1, int64_t(src_bytes / (double(v) * 1048576.0) + 0.5));
     }
+#endif
     const int64_t rows_per_band = std::max<int64_t>(1, (by + want_bands - 1) / want_bands);
     const int nbands = int((by + rows_per_band - 1) / rows_per_band);
     constexpr int kStreams = 3;
@@ -522,27 +527,61 @@ int astc_b200_save_astc(const char *path, int xdim, int ydim, int xsize, int ysi
     return astc_save::write_file(path, xdim, ydim, xsize, ysize, blocks, bufsz) ? ASTC_B200_OK : ASTC_B200_ERR_IO;
 }
 
+int astc_b200_save_astc_slice(const char *path, int xdim, int ydim, int xsize, int ysize, size_t block_byte_offset,
+                              const uint8_t *blocks, size_t nbytes, int write_header)
+{
+    if (!path || (!blocks && nbytes) || xdim <= 0 || ydim <= 0 || xsize < 0 || ysize < 0) return ASTC_B200_ERR_INVALID_ARGUMENT;
+    const size_t payload = size_t((xsize + xdim - 1) / xdim) * size_t((ysize + ydim - 1) / ydim) * ASTC_B200_BLOCK_BYTES;
+    if (block_byte_offset > payload || nbytes > payload - block_byte_offset) return ASTC_B200_ERR_INVALID_ARGUMENT;
+    const int fd = ::open(path, O_WRONLY | O_CREAT, 0644);          // no O_TRUNC: other ranks may have written already
+    if (fd < 0) return ASTC_B200_ERR_IO;
+    bool ok = ::ftruncate(fd, off_t(sizeof(astc_header) + payload)) == 0;   // idempotent: every rank sets the same size
+    auto put = [&](const void *src, size_t n, off_t at) {
+        const uint8_t *p = static_cast<const uint8_t *>(src);
+        while (ok && n) {
+            const ssize_t w = ::pwrite(fd, p, n, at);
+            if (w <= 0) { ok = false; break; }
+            p += w; n -= size_t(w); at += w;
+        }
+    };
+    if (write_header) {
+        const astc_header h = astc_save::make_header(xdim, ydim, xsize, ysize);
+        put(&h, sizeof h, 0);
+    }
+    put(blocks, nbytes, off_t(sizeof(astc_header) + block_byte_offset));
+    ok = (::close(fd) == 0) && ok;
+    return ok ? ASTC_B200_OK : ASTC_B200_ERR_IO;
+}
+
 int astc_b200_load_astc(const char *path, int *xdim, int *ydim, int *xsize, int *ysize, uint8_t **blocks, size_t *bufsz)
 {
     if (!path || !blocks || !bufsz) return ASTC_B200_ERR_INVALID_ARGUMENT;
     *blocks = nullptr; *bufsz = 0;
     std::FILE *f = std::fopen(path, "rb");
     if (!f) return ASTC_B200_ERR_IO;
-    astc_header hdr;
+    astc_header hdr{};
     int rc = ASTC_B200_OK;
     if (std::fread(&hdr, 1, sizeof hdr, f) != sizeof hdr) rc = ASTC_B200_ERR_BAD_IMAGE;
-    const uint32_t magic = uint32_t(hdr.magic[0]) | (uint32_t(hdr.magic[1]) << 8) | (uint32_t(hdr.magic[2]) << 16) |
-                           (uint32_t(hdr.magic[3]) << 24);
-    if (rc == ASTC_B200_OK && (magic != ASTC_B200_MAGIC || hdr.blockdim_x == 0 || hdr.blockdim_y == 0 || hdr.blockdim_z == 0))
-        rc = ASTC_B200_ERR_BAD_IMAGE;
+    if (rc == ASTC_B200_OK) {
+        const uint32_t magic = uint32_t(hdr.magic[0]) | (uint32_t(hdr.magic[1]) << 8) | (uint32_t(hdr.magic[2]) << 16) |
+                               (uint32_t(hdr.magic[3]) << 24);
+        const int zs = hdr.zsize[0] | (hdr.zsize[1] << 8) | (hdr.zsize[2] << 16);
+        // this encoder's files are 2-D (astc_save.h:60-66 writes blockdim_z = zsize = 1); a 3-D file is refused, not flattened
+        if (magic != ASTC_B200_MAGIC || hdr.blockdim_x == 0 || hdr.blockdim_y == 0 || hdr.blockdim_z != 1 || zs != 1)
+            rc = ASTC_B200_ERR_BAD_IMAGE;
+    }
     if (rc == ASTC_B200_OK) {
         const int xs = hdr.xsize[0] | (hdr.xsize[1] << 8) | (hdr.xsize[2] << 16);
         const int ys = hdr.ysize[0] | (hdr.ysize[1] << 8) | (hdr.ysize[2] << 16);
-        const int zs = hdr.zsize[0] | (hdr.zsize[1] << 8) | (hdr.zsize[2] << 16);
-        const size_t nb = size_t((xs + hdr.blockdim_x - 1) / hdr.blockdim_x) * size_t((ys + hdr.blockdim_y - 1) / hdr.blockdim_y) *
-                          size_t((zs + hdr.blockdim_z - 1) / hdr.blockdim_z);
-        uint8_t *buf = static_cast<uint8_t *>(std::malloc(nb * 16u + 1u));
-        if (!buf) rc = ASTC_B200_ERR_OUT_OF_MEMORY;
+        const size_t nb = size_t((xs + hdr.blockdim_x - 1) / hdr.blockdim_x) * size_t((ys + hdr.blockdim_y - 1) / hdr.blockdim_y);
+        // the payload must be there before anything is allocated for it (24-bit sizes allow 2^44 blocks)
+        long have = -1;
+        if (std::fseek(f, 0, SEEK_END) == 0) have = std::ftell(f);
+        if (have < 0 || size_t(have) < sizeof hdr || (size_t(have) - sizeof hdr) / 16u < nb || std::fseek(f, long(sizeof hdr), SEEK_SET) != 0)
+            rc = ASTC_B200_ERR_BAD_IMAGE;
+        uint8_t *buf = rc == ASTC_B200_OK ? static_cast<uint8_t *>(std::malloc(nb * 16u + 1u)) : nullptr;
+        if (rc != ASTC_B200_OK) {}
+        else if (!buf) rc = ASTC_B200_ERR_OUT_OF_MEMORY;
         else if (std::fread(buf, 1, nb * 16u, f) != nb * 16u) { std::free(buf); rc = ASTC_B200_ERR_BAD_IMAGE; }
         else {
             *blocks = buf; *bufsz = nb * 16u;

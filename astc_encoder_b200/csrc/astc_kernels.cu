@@ -484,8 +484,11 @@ static int choose_passes(uint64_t total_blocks, int threads, int ctas_per_sm, in
         if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
             sm_count = 148;
     }
-    const char *force = getenv("ASTC_B200_PASSES");                       // tuning hook (tools/passes_sweep.sh)
+#ifdef ASTC_TUNING_HOOKS
+    // experiment builds only (tools/variants.py build hooks=ASTC_TUNING_HOOKS): never compiled into the product library
+    const char *force = getenv("ASTC_B200_PASSES");
     if (force && atoi(force) > 0) return atoi(force) > kMaxPasses ? kMaxPasses : atoi(force);
+#endif
     const uint64_t resident = uint64_t(sm_count) * uint64_t(ctas_per_sm);
     const uint64_t want = total_blocks / (resident * 3u * uint64_t(threads));
     return want < 1 ? 1 : want > uint64_t(max_passes) ? max_passes : int(want);

@@ -21,7 +21,7 @@ from typing import Callable, List, Optional, Sequence
 
 import numpy as np
 
-from . import BLOCK_BYTES, band, block_counts, block_dim, encode_option, output_size
+from . import BLOCK_BYTES, band, block_dim, encode_option, output_size
 
 __all__ = ["Band", "band_plan", "assign_textures", "encode_band", "write_astc_sharded", "gather_blocks"]
 
@@ -74,25 +74,14 @@ def encode_band(rgba: np.ndarray, option: encode_option, rank: int, world: int,
 
 def write_astc_sharded(path: str, width: int, height: int, option: encode_option, b: Band, blocks: np.ndarray,
                        rank: int) -> None:
-    """Every rank writes its slice of ONE .astc file at its byte offset; rank 0 also writes the
-    16-byte header (astc_save.h:52-76) and sizes the file.  Callers barrier before reading."""
-    from . import lib
+    """Every rank writes its slice of ONE .astc file at its byte offset; rank 0 also writes the 16-byte
+    header (astc_save.h:52-76).  Safe in any order and without a barrier between the writers: the file
+    is created without truncation, every rank sets the same final size, and the ranges are disjoint
+    (astc_b200_save_astc_slice).  Readers barrier after the last writer, as for any shared file."""
+    from . import save_astc_slice
     d = block_dim(option)
-    total = ASTC_HEADER_BYTES + output_size(width, height, option)
-    if rank == 0:
-        import ctypes as C
-        hdr_only = np.zeros(0, np.uint8)
-        rc = lib().astc_b200_save_astc(str(path).encode(), d, d, width, height, hdr_only.ctypes.data, 0)
-        if rc != 0:
-            raise OSError(f"cannot create {path}")
-        os.truncate(path, total)
-    fd = os.open(path, os.O_WRONLY | os.O_CREAT)
-    try:
-        data = np.ascontiguousarray(blocks, dtype=np.uint8).tobytes()
-        if data:
-            os.pwrite(fd, data, ASTC_HEADER_BYTES + b.byte_offset)
-    finally:
-        os.close(fd)
+    save_astc_slice(path, d, d, width, height, b.byte_offset, np.ascontiguousarray(blocks, dtype=np.uint8).reshape(-1),
+                    write_header=(rank == 0))
 
 
 def gather_blocks(local: np.ndarray, width: int, height: int, option: encode_option, dst: int = 0):

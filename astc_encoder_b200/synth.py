@@ -40,28 +40,36 @@ def _splitmix64(x: torch.Tensor) -> torch.Tensor:
     return x ^ _lsr(x, 31)
 
 
-def synth_rgba(width: int, height: int, seed: int, device="cpu", rows_per_chunk: int = 1024) -> torch.Tensor:
-    """(H, W, 4) uint8."""
-    out = torch.empty((height, width, 4), dtype=torch.uint8, device=device)
+def synth_rgba(width: int, height: int, seed: int, device="cpu", rows_per_chunk: int = 1024,
+               row0: int = 0, rows: int | None = None) -> torch.Tensor:
+    """(H, W, 4) uint8.  `row0` / `rows` produce only that slab of texel rows of the same
+    width x height image (a rank's band of a sharded texture): texels depend on their absolute position."""
+    if rows is None:
+        row0, rows = 0, height
+    out = torch.empty((rows, width, 4), dtype=torch.uint8, device=device)
+    for y0 in range(row0, row0 + rows, rows_per_chunk):
+        n = min(rows_per_chunk, row0 + rows - y0)
+        out[y0 - row0:y0 - row0 + n] = _synth_rows(width, height, seed, device, y0, y0 + n)
+    return out
+
+
+def _synth_rows(width: int, height: int, seed: int, device, y0: int, y1: int) -> torch.Tensor:
+    """Texel rows [y0, y1) of synth_rgba(width, height, seed)."""
+    out = torch.empty((y1 - y0, width, 4), dtype=torch.uint8, device=device)
     xs = torch.arange(width, device=device, dtype=torch.float32)
     xi = torch.arange(width, device=device, dtype=torch.int64)
     rng = (seed * 2654435761) & 0xFFFFFFFF
-    params = []
+    ys = torch.arange(y0, y1, device=device, dtype=torch.float32)[:, None]
+    yi = torch.arange(y0, y1, device=device, dtype=torch.int64)[:, None]
+    lin = (yi * width + xi[None, :]) * 4
     for c in range(4):
-        fx = 1 + ((rng >> (4 * c)) & 3)
-        fy = 1 + ((rng >> (4 * c + 2)) & 3)
+        fx = float(1 + ((rng >> (4 * c)) & 3))
+        fy = float(1 + ((rng >> (4 * c + 2)) & 3))
         phase = 2.0 * math.pi * (((rng >> (16 + 3 * c)) & 7) / 8.0)
-        params.append((float(fx), float(fy), phase))
-    for y0 in range(0, height, rows_per_chunk):
-        y1 = min(height, y0 + rows_per_chunk)
-        ys = torch.arange(y0, y1, device=device, dtype=torch.float32)[:, None]
-        yi = torch.arange(y0, y1, device=device, dtype=torch.int64)[:, None]
-        lin = (yi * width + xi[None, :]) * 4
-        for c, (fx, fy, phase) in enumerate(params):
-            base = 128.0 + 96.0 * torch.sin((2.0 * math.pi / max(width, 1)) * (xs[None, :] * fx + ys * fy) + phase)
-            h = _splitmix64((lin + c) ^ _i64(seed))
-            noise = (_lsr(h, 40) & 0xFFFF).to(torch.float32) * (32.0 / 65535.0) - 16.0
-            out[y0:y1, :, c] = torch.clamp(torch.round(base + noise), 0, 255).to(torch.uint8)
+        base = 128.0 + 96.0 * torch.sin((2.0 * math.pi / max(width, 1)) * (xs[None, :] * fx + ys * fy) + phase)
+        h = _splitmix64((lin + c) ^ _i64(seed))
+        noise = (_lsr(h, 40) & 0xFFFF).to(torch.float32) * (32.0 / 65535.0) - 16.0
+        out[:, :, c] = torch.clamp(torch.round(base + noise), 0, 255).to(torch.uint8)
     return out
 
 

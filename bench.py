@@ -313,6 +313,12 @@ def run_b200(args) -> int:
     del d_probe_in, d_probe_out
     e2e_value = world * texels / e2e_s / 1e6
 
+    # ---- BASELINE config 5 as written: ONE 16384^2 texture in block-row bands + 512 mip chains dealt by texture ----
+    cfg5 = None
+    if not args.no_others:
+        del h_in, h_out, h_in_np, h_out_np
+        cfg5 = config5(torch, dist, A, synth, dev, rank, world, barrier, max_over_ranks, tex if world == 1 else None, out, args)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -361,22 +367,41 @@ def run_b200(args) -> int:
     if world == 1 and not args.no_cpu:
         from oracle import oracle as O
         O.lib()
+        import numpy as np
+        ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        # timing: the reference arm's crop (16384 x 1024 texels), one warm-up, median of 5
+        crop_rows = 1024
+        crop = tex[:crop_rows].cpu().numpy()
+
+        def oracle_rate(rows_texels, threads, runs):
+            O.encode_rows(crop, 0, rows_texels // 4, block_dim=4, threads=threads)          # warm-up
+            ts, used = [], threads
+            for _ in range(runs):
+                t0 = time.perf_counter()
+                _, used = O.encode_rows(crop, 0, rows_texels // 4, block_dim=4, threads=threads)
+                ts.append(time.perf_counter() - t0)
+            ts.sort()
+            return W16K * rows_texels / ts[len(ts) // 2] / 1e6, int(used), ts
+
+        mt, used, ts = oracle_rate(crop_rows, ncpu, 5)
+        st_rows = 128                                               # single thread: 16384 x 128 texels per run
+        st, _, _ = oracle_rate(st_rows, 1, 3)
+        line["cpu_baseline"] = {"value": round(mt, 2), "unit": UNIT, "cores": used, "kind": "port",
+                                "sample": f"block rows 0..{crop_rows // 4 - 1} ({W16K}x{crop_rows} texels) of the same texture, "
+                                          "oracle/astc_oracle.c with OpenMP; 1 warm-up, median of 5",
+                                "runs_ms": [round(t * 1e3, 1) for t in ts],
+                                "single_thread": {"value": round(st, 2), "unit": UNIT, "cores": 1,
+                                                  "sample": f"{W16K}x{st_rows} texels, 1 warm-up, median of 3"}}
+        # parity: 4 194 304 blocks of the GPU output against the oracle
         rows_texels = 4096
         sample = tex[:rows_texels].cpu().numpy()
-        t0 = time.perf_counter()
-        ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-        want, used = O.encode_rows(sample, 0, rows_texels // 4, block_dim=4, threads=ncpu)
-        dt = time.perf_counter() - t0
+        want, _ = O.encode_rows(sample, 0, rows_texels // 4, block_dim=4, threads=ncpu)
         got = out[: want.shape[0]].cpu().numpy()
         same = int((got == want).all(axis=1).sum())
-        line["cpu_baseline"] = {"value": round(W16K * rows_texels / dt / 1e6, 2), "unit": UNIT, "cores": int(used),
-                                "kind": "port", "sample": f"block rows 0..{rows_texels // 4 - 1} ({W16K}x{rows_texels} texels) "
-                                "of the same texture, oracle/astc_oracle.c with OpenMP"}
         line["parity"] = {"blocks_checked": int(want.shape[0]), "bit_identical": same}
         # decoded PSNR (per channel, dB) of the GPU's blocks (device decoder) and of the oracle's blocks
         # (oracle decoder) against the source, on the first 1024 texel rows of the sample: the metric's
         # "decoded PSNR delta vs ref" (0 when every block is bit-identical)
-        import numpy as np
         prow = 1024
         nblk = (prow // 4) * (W16K // 4)
         dec_gpu = A.decode_astc(out[:nblk], W16K, prow, 4).cpu().numpy()
@@ -390,11 +415,129 @@ def run_b200(args) -> int:
     # ---- the other BASELINE.json configs, kernel-only, L2 flushed between launches ----
     if world == 1 and not args.no_others:
         line["others"] = other_configs(torch, A, synth, dev, peak)
+    if cfg5 is not None:
+        line["config5"] = cfg5
 
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def config5(torch, dist, A, synth, dev, rank, world, barrier, max_over_ranks, full_tex, full_out, args):
+    """BASELINE.json configs[4], sharded the two ways north_star names, device-resident, no collective on the
+    data path: (a) ONE 16384x16384 texture cut into `world` contiguous block-row bands (astc_b200_band), every
+    rank encoding its band into its slice of the output; (b) 512 2048x2048 12-level mip chains dealt out whole
+    by sharding.assign_textures (longest first), one batch launch per rank.  Strong scaling: the total work is
+    fixed.  Times are CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.
+    Both outputs are checked byte for byte ON THE GPUS against the single-GPU encode of the same input."""
+    from astc_encoder_b200 import sharding
+    opt = A.encode_option()
+    steps, warm = max(5, min(args.steps, 20)), 3
+    stream = torch.cuda.current_stream()
+
+    def all_true(flag: bool) -> bool:
+        if world == 1:
+            return bool(flag)
+        t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    def timed(fn):
+        for _ in range(warm):
+            fn()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(steps):
+            fn()
+        b.record(stream)
+        torch.cuda.synchronize()
+        barrier()
+        return max_over_ranks(a.elapsed_time(b) / steps)
+
+    # ---- (a) one texture, `world` bands ----
+    band = sharding.band_plan(W16K, W16K, opt, world)[rank]
+    slab = full_tex if world == 1 else synth.synth_rgba(W16K, W16K, synth.SEED_CFG5, device=dev, row0=band.y0, rows=band.rows)
+    band_out = torch.empty((band.nbytes // 16, 16), dtype=torch.uint8, device=dev)
+    band_ms = timed(lambda: A.encode_astc(slab, opt, out=band_out, stream=stream))
+    # the single-GPU encode of the whole texture, on this rank's GPU (deterministic, so the same on every rank)
+    if world > 1:
+        full_tex = synth.synth_rgba(W16K, W16K, synth.SEED_CFG5, device=dev)
+        full_out = torch.empty((W16K // 4 * (W16K // 4), 16), dtype=torch.uint8, device=dev)
+    single_ms = None
+    if world > 1:
+        for _ in range(warm):
+            A.encode_astc(full_tex, opt, out=full_out, stream=stream)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(steps):
+            A.encode_astc(full_tex, opt, out=full_out, stream=stream)
+        b.record(stream)
+        torch.cuda.synchronize()
+        single_ms = max_over_ranks(a.elapsed_time(b) / steps)
+    else:
+        A.encode_astc(full_tex, opt, out=full_out, stream=stream)
+        torch.cuda.synchronize()
+    lo = band.byte_offset // 16
+    band_same = all_true(torch.equal(full_out[lo:lo + band.nbytes // 16], band_out))
+    if world > 1:
+        del full_tex, full_out
+    del slab
+    texels_a = W16K * W16K
+
+    # ---- (b) 512 mip chains dealt by texture ----
+    chains = args.chains
+    chain_texels = sum(max(1, 2048 >> l) ** 2 for l in range(12))
+    mine = sharding.assign_textures([chain_texels] * chains, world)[rank]
+    srcs = []
+    for i in mine:
+        srcs.extend(A.mip_chain(synth.synth_rgba(2048, 2048, synth.SEED_BATCH + i, device=dev)))     # device 2x2 box filter
+    batch = A.Batch(srcs, opt)
+    batch_ms = timed(lambda: batch.encode(stream=stream))
+    outs = batch.encode(stream=stream)
+    torch.cuda.synchronize()
+    # byte check against the single-texture path (one encode_astc launch per level) on this GPU, and a checksum
+    # of checksums that does not depend on how the chains were dealt
+    same = True
+    csum = torch.zeros((), dtype=torch.int64, device=dev)
+    for src, o in zip(srcs, outs):
+        same = same and bool(torch.equal(A.encode_astc(src, opt, stream=stream), o))
+        csum += o.view(torch.int64).sum()
+    if world > 1:
+        dist.all_reduce(csum, op=dist.ReduceOp.SUM)
+    batch_same = all_true(same)
+    texels_b = chains * chain_texels
+
+    # ---- the whole of config 5 in one step: band launch + batch launch per rank ----
+    slab2 = synth.synth_rgba(W16K, W16K, synth.SEED_CFG5, device=dev, row0=band.y0, rows=band.rows)
+
+    def both():
+        A.encode_astc(slab2, opt, out=band_out, stream=stream)
+        batch.encode(stream=stream)
+
+    both_ms = timed(both)
+    launches_per_step = 2
+    total_blocks = int(batch.total_blocks)
+    batch.close()
+    del srcs, outs, slab2
+    res = {
+        "workload": "BASELINE configs[4]: 16384x16384 RGBA8 4x4 RGB + 512 x 2048x2048 12-level mip chains, device-resident",
+        "scaling": "strong", "n_gpus": world, "steps": steps, "unit": UNIT,
+        "band": {"what": f"ONE 16384x16384 texture in {world} block-row band(s) (astc_b200_band), one launch per rank",
+                 "ms": round(band_ms, 4), "value": round(texels_a / band_ms / 1e3, 1),
+                 "bytes_identical_to_single_gpu_encode": band_same, "blocks_per_rank": band.nbytes // 16},
+        "batch": {"what": f"{chains} mip chains dealt whole by sharding.assign_textures (LPT), ONE batch launch per rank",
+                  "ms": round(batch_ms, 4), "value": round(texels_b / batch_ms / 1e3, 1), "chains_per_rank": len(mine),
+                  "blocks_this_rank": total_blocks, "bytes_identical_to_per_texture_encode": batch_same,
+                  "checksum_of_all_blocks": f"{int(csum.item()) & 0xFFFFFFFFFFFFFFFF:016x}"},
+        "both": {"what": "band launch + batch launch per step (the whole of configs[4])", "ms": round(both_ms, 4),
+                 "value": round((texels_a + texels_b) / both_ms / 1e3, 1), "launches_per_step_per_rank": launches_per_step},
+    }
+    if single_ms is not None:
+        res["band"]["single_gpu_ms_same_run"] = round(single_ms, 4)
+        res["band"]["strong_scaling_efficiency"] = round(single_ms / (world * band_ms), 4)
+    return res
 
 
 def other_configs(torch, A, synth, dev, peak):
@@ -418,16 +561,6 @@ def other_configs(torch, A, synth, dev, peak):
         A.encode_option(is6x6=True, has_alpha=True, srgb=True), 6)
     one("4096x4096 normal map, -norm -4x4", synth.synth_normal(4096, 4096, synth.SEED_CFG4, device=dev),
         A.encode_option(is_normal_map=True), 4)
-    # batch of 2048x2048 mip chains in one launch over a prefix-summed block table
-    chains = 512                                                 # BASELINE config 5: 11.45 GB of texels resident, 178 957 824 blocks
-    srcs = []
-    for i in range(chains):
-        srcs.extend(A.mip_chain(synth.synth_rgba(2048, 2048, synth.SEED_BATCH + i, device=dev)))   # device 2x2 box filter
-    batch = A.Batch(srcs, A.encode_option())
-    ms = _time_launches(torch, lambda: batch.encode(), 10, 3, None)
-    res.append({"workload": f"{chains} x 2048x2048 12-level mip chains, 4x4 RGB, ONE launch", "value": round(batch.total_texels / ms / 1e3, 1),
-                "unit": UNIT, "kernel_ms": round(ms, 4), "textures": len(srcs), "blocks": int(batch.total_blocks)})
-    batch.close()
     return res
 
 
@@ -439,7 +572,8 @@ def main() -> int:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU oracle baseline / parity sample")
-    ap.add_argument("--no-others", action="store_true", help="skip the secondary configs")
+    ap.add_argument("--no-others", action="store_true", help="skip the secondary configs (incl. config 5)")
+    ap.add_argument("--chains", type=int, default=512, help="mip chains in the config-5 batch (default: BASELINE's 512)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3                                          # timing rule: W >= 3

@@ -185,7 +185,15 @@ ASTC_B200_API int astc_b200_stream_synchronize(void *cuda_stream);
 /* astc_header + save_astc (astc_save.h:5-14,52-76), byte-exact. */
 ASTC_B200_API int astc_b200_save_astc(const char *path, int xdim, int ydim, int xsize, int ysize,
                                       const uint8_t *blocks, size_t bufsz);
-/* Matching reader. *blocks is malloc'ed; release with astc_b200_free_host_buffer. */
+/* Multi-GPU / multi-process variant of save_astc: writes `nbytes` of blocks at `block_byte_offset` of the
+ * payload (astc_b200_band) of the .astc file for an xsize x ysize image, creating and sizing the file if
+ * need be; with write_header != 0 also the 16-byte header.  Never truncates existing content, so the
+ * ranks sharing one file may call it in any order without a barrier (each writes a disjoint range). */
+ASTC_B200_API int astc_b200_save_astc_slice(const char *path, int xdim, int ydim, int xsize, int ysize,
+                                            size_t block_byte_offset, const uint8_t *blocks, size_t nbytes,
+                                            int write_header);
+/* Matching reader (2-D files: blockdim_z == 1 and zsize == 1). *blocks is malloc'ed; release with
+ * astc_b200_free_host_buffer. */
 ASTC_B200_API int astc_b200_load_astc(const char *path, int *xdim, int *ydim, int *xsize, int *ysize,
                                       uint8_t **blocks, size_t *bufsz);
 /* stbi_load(..., STBI_rgb_alpha) with optional vertical flip (main.cpp:24-25):
