@@ -356,6 +356,9 @@ static inline float clamp255(float v)
  * normal range, checked by the generator and again by tests/test_gpu_edges.py on the device).
  * Every argument the encoder feeds them is positive and normal (>= 1e-20). */
 static const int8_t *g_rcp_delta = NULL, *g_rsq_delta = NULL;
+static unsigned g_variant = 0;           /* sensitivity switches, tools/pin_sensitivity.py only */
+
+void astc_oracle_set_variant(unsigned flags) { g_variant = flags; }
 
 void astc_oracle_set_mufu_tables(const int8_t *rcp_delta, const int8_t *rsq_delta)
 {
@@ -370,6 +373,7 @@ float astc_oracle_mufu_rcp(float x)
 {
     const uint32_t b = f2u(x);
     const float base = (float)(1.0 / (double)x);
+    if (g_variant & ASTC_ORACLE_VAR_EXACT_RCP_RSQ) return base;
     if (!g_rcp_delta) return u2f(0x7FC00000u);                 /* tables not loaded: poison, never a silent fallback */
     return u2f(f2u(base) + (uint32_t)(int32_t)g_rcp_delta[b & 0x7FFFFFu]);
 }
@@ -378,6 +382,7 @@ float astc_oracle_mufu_rsq(float x)
 {
     const uint32_t b = f2u(x), parity = ((b >> 23) + 1u) & 1u;  /* biased exponent 127 ([1,2)) -> 0 */
     const float base = (float)(1.0 / sqrt((double)x));
+    if (g_variant & ASTC_ORACLE_VAR_EXACT_RCP_RSQ) return base;
     if (!g_rsq_delta) return u2f(0x7FC00000u);
     return u2f(f2u(base) + (uint32_t)(int32_t)g_rsq_delta[(parity << 23) | (b & 0x7FFFFFu)]);
 }
@@ -401,33 +406,87 @@ static void power_iteration(const float m[16], float v[4])
     }
 }
 
-/* principal_component_analysis + find_min_max (ASTC_Encode.hlsl:108-168). */
-static void pca_endpoints(const float (*raw)[4], int bs, int has_alpha,
-                          float e0[4], float e1[4], astc_oracle_trace *tr)
+/* texel*255 - base: one FMA in the canonical arithmetic (the golden prefers it: DESIGN.md 2). */
+static inline float deviation(float raw, float base)
 {
-    float sum[4] = {0, 0, 0, 0}, mean[4], cov[16], axis[4];
-    const float inv_n = 1.0f / (float)bs, inv_n1 = 1.0f / (float)(bs - 1);
-    float lo = 1e31f, hi = -1e31f, s0, s1;
-    int k, i, j;
+    if (g_variant & ASTC_ORACLE_VAR_UNFUSED_DEV) return raw * 255.0f - base;
+    return fmaf(raw, 255.0f, -base);
+}
 
+/* pt_mean of principal_component_analysis / max_accumulation_pixel_direction (:142-147, :172-178). */
+static void block_mean(const float (*raw)[4], int bs, float mean[4])
+{
+    float sum[4] = {0, 0, 0, 0};
+    const float inv_n = 1.0f / (float)bs;
+    int k, i;
     for (k = 0; k < bs; ++k)
         for (i = 0; i < 4; ++i) sum[i] = sum[i] + raw[k][i] * 255.0f;
-    for (i = 0; i < 4; ++i) mean[i] = sum[i] * inv_n;
+    for (i = 0; i < 4; ++i)
+        mean[i] = (g_variant & ASTC_ORACLE_VAR_TRUE_DIVISION) ? sum[i] / (float)bs : sum[i] * inv_n;
+}
 
+/* principal_component_analysis up to the axis (ASTC_Encode.hlsl:149-164). */
+static void pca_axis(const float (*raw)[4], int bs, const float mean[4], float cov[16], float axis[4])
+{
+    const float inv_n1 = 1.0f / (float)(bs - 1);
+    int k, i, j;
     for (i = 0; i < 16; ++i) cov[i] = 0.0f;
     for (k = 0; k < bs; ++k) {
         float d[4];
-        for (i = 0; i < 4; ++i) d[i] = fmaf(raw[k][i], 255.0f, -mean[i]);
+        for (i = 0; i < 4; ++i) d[i] = deviation(raw[k][i], mean[i]);
         for (i = 0; i < 4; ++i)
             for (j = 0; j < 4; ++j) cov[4 * i + j] = fmaf(d[i], d[j], cov[4 * i + j]);
     }
-    for (i = 0; i < 16; ++i) cov[i] = cov[i] * inv_n1;
-
+    for (i = 0; i < 16; ++i)
+        cov[i] = (g_variant & ASTC_ORACLE_VAR_TRUE_DIVISION) ? cov[i] / (float)(bs - 1) : cov[i] * inv_n1;
     power_iteration(cov, axis);
+}
+
+/* max_accumulation_pixel_direction up to the axis (ASTC_Encode.hlsl:180-223): for each channel c the
+ * sum of the deviations of the texels that lie above the mean in c; the longest of the four sums
+ * (three without alpha; strict >, so ties keep the earlier channel) is the direction, normalised
+ * unless shorter than SMALL_VALUE.  `sum += cond ? dt : 0` adds an exact zero when the condition
+ * fails, so it is restated as a conditional add. */
+static void accumulation_axis(const float (*raw)[4], int bs, int has_alpha, const float mean[4], float axis[4])
+{
+    float sum[4][4] = {{0}}, best;
+    int k, i, c, pick = 0;
+    for (k = 0; k < bs; ++k) {
+        float d[4];
+        for (i = 0; i < 4; ++i) d[i] = deviation(raw[k][i], mean[i]);
+        for (c = 0; c < 4; ++c)
+            if (d[c] > 0.0f)
+                for (i = 0; i < 4; ++i) sum[c][i] = sum[c][i] + d[i];
+    }
+    best = dot4(sum[0], sum[0]);
+    for (c = 1; c < (has_alpha ? 4 : 3); ++c) {
+        const float dc = dot4(sum[c], sum[c]);
+        if (dc > best) { best = dc; pick = c; }
+    }
+    memcpy(axis, sum[pick], sizeof sum[pick]);
+    if (!(sqrtf(best) < SMALL_VALUE)) {                           /* safe normalize (:219-221) */
+        const float inv = astc_oracle_mufu_rsq(best);
+        for (i = 0; i < 4; ++i) axis[i] = axis[i] * inv;
+    }
+}
+
+/* principal_component_analysis / max_accumulation_pixel_direction + find_min_max
+ * (ASTC_Encode.hlsl:108-227). */
+static void pca_endpoints(const float (*raw)[4], int bs, int has_alpha, int axis_method,
+                          float e0[4], float e1[4], astc_oracle_trace *tr)
+{
+    float mean[4], cov[16], axis[4];
+    float lo = 1e31f, hi = -1e31f, s0, s1;
+    int k, i;
+
+    block_mean(raw, bs, mean);
+    memset(cov, 0, sizeof cov);
+    if (axis_method == 1) accumulation_axis(raw, bs, has_alpha, mean, axis);
+    else pca_axis(raw, bs, mean, cov, axis);
 
     for (k = 0; k < bs; ++k) {
         float d[4], t;
-        for (i = 0; i < 4; ++i) d[i] = fmaf(raw[k][i], 255.0f, -mean[i]);
+        for (i = 0; i < 4; ++i) d[i] = deviation(raw[k][i], mean[i]);
         t = dot4(d, axis);
         lo = fminf(lo, t);
         hi = fmaxf(hi, t);
@@ -485,16 +544,22 @@ static void project_weights(const float (*raw)[4], int dim, const float e0[4],
     for (i = 0; i < 16; ++i) {
         float d[4], w;
         if (dim == 4) {
-            for (c = 0; c < 4; ++c) d[c] = fmaf(raw[i][c], 255.0f, -e0[c]);
+            for (c = 0; c < 4; ++c) d[c] = deviation(raw[i][c], e0[c]);
         } else {
             int idx[4];
             float wt[4];
             grid_taps(i, idx, wt);
             for (c = 0; c < 4; ++c) {
                 float s = (raw[idx[0]][c] * 255.0f) * wt[0];
-                s = fmaf(raw[idx[1]][c] * 255.0f, wt[1], s);
-                s = fmaf(raw[idx[2]][c] * 255.0f, wt[2], s);
-                s = fmaf(raw[idx[3]][c] * 255.0f, wt[3], s);
+                if (g_variant & ASTC_ORACLE_VAR_UNFUSED_SAMPLE) {
+                    s = s + (raw[idx[1]][c] * 255.0f) * wt[1];
+                    s = s + (raw[idx[2]][c] * 255.0f) * wt[2];
+                    s = s + (raw[idx[3]][c] * 255.0f) * wt[3];
+                } else {
+                    s = fmaf(raw[idx[1]][c] * 255.0f, wt[1], s);
+                    s = fmaf(raw[idx[2]][c] * 255.0f, wt[2], s);
+                    s = fmaf(raw[idx[3]][c] * 255.0f, wt[3], s);
+                }
                 d[c] = s - e0[c];
             }
         }
@@ -521,7 +586,7 @@ void astc_oracle_encode_block(const float (*raw)[4], const astc_oracle_opt *opt,
     int i;
 
     ensure_tables();
-    pca_endpoints(raw, bs, has_alpha, e0, e1, tr);
+    pca_endpoints(raw, bs, has_alpha, opt->axis_method == 1 ? 1 : 0, e0, e1, tr);
 
     /* encode_color (:233-245) + endpoint_ise (:475-489) */
     for (i = 0; i < 4; ++i) {
@@ -570,6 +635,10 @@ void astc_oracle_unorm_lut(int srgb, float out[256])
             double x = (double)c / 255.0;
             double y = x <= 0.04045 ? x / 12.92 : pow((x + 0.055) / 1.055, 2.4);
             out[c] = (float)y;
+            if (g_variant & ASTC_ORACLE_VAR_SRGB_POWF) {
+                const float xf = (float)c / 255.0f;
+                out[c] = xf <= 0.04045f ? xf / 12.92f : powf((xf + 0.055f) / 1.055f, 2.4f);
+            }
         }
     }
 }

@@ -12,6 +12,8 @@
  *   ASTC_Encode.hlsl:139-168   principal_component_analysis -> pca_endpoints
  *   ASTC_Encode.hlsl:93-106    eigen_vector                 -> power_iteration
  *   ASTC_Encode.hlsl:108-137   find_min_max                 -> pca_endpoints
+ *   ASTC_Encode.hlsl:170-227   max_accumulation_pixel_direction (the alternative axis heuristic the
+ *                              reference carries with its call commented out at :514) -> accumulation_axis
  *   ASTC_Encode.hlsl:233-245   encode_color                 -> astc_oracle_encode_block
  *   ASTC_Encode.hlsl:316-393   weights                      -> project_weights
  *   ASTC_Encode.hlsl:400-473   assemble_block/_blockmode    -> assemble
@@ -56,7 +58,21 @@ typedef struct astc_oracle_opt {
     int is_normal_map;  /* IS_NORMALMAP (astc_encode.h:59)                */
     int srgb;           /* texture format _UNORM_SRGB (main.cpp:38,214);  */
                         /* ignored when is_normal_map is set              */
+    int axis_method;    /* 0: principal_component_analysis (:139-168, what the reference ships);          */
+                        /* 1: max_accumulation_pixel_direction (:170-227, commented out at :514)           */
 } astc_oracle_opt;
+
+/* Sensitivity switches (tools/pin_sensitivity.py ONLY): each replaces one modelling choice that no
+ * reference fixture pins by its plausible alternative, so the number of blocks it decides can be
+ * measured.  0 = the canonical arithmetic; process-wide, not thread-safe against running encodes. */
+enum {
+    ASTC_ORACLE_VAR_TRUE_DIVISION = 1,   /* mean = sum / BS and cov / (BS-1) as IEEE divisions (:147,162), not x RN(1/n) */
+    ASTC_ORACLE_VAR_UNFUSED_SAMPLE = 2,  /* 6x6 sample_texel (:307-314): every product and sum rounded, no FMA          */
+    ASTC_ORACLE_VAR_SRGB_POWF = 4,       /* sRGB decode evaluated in float (powf) instead of double rounded once        */
+    ASTC_ORACLE_VAR_EXACT_RCP_RSQ = 8,   /* correctly rounded 1/x and 1/sqrt(x) instead of the MUFU approximations     */
+    ASTC_ORACLE_VAR_UNFUSED_DEV = 16     /* texel*255 rounded before the subtraction of mean / e0 (no FMA)             */
+};
+void astc_oracle_set_variant(unsigned flags);
 
 /* Diagnostics of one block encode (unrounded endpoints, raw weights). */
 typedef struct astc_oracle_trace {

@@ -19,7 +19,7 @@ _SO = _HERE / "_build" / "libastc_oracle.so"
 
 class OracleOpt(C.Structure):
     _fields_ = [("block_dim", C.c_int), ("has_alpha", C.c_int),
-                ("is_normal_map", C.c_int), ("srgb", C.c_int)]
+                ("is_normal_map", C.c_int), ("srgb", C.c_int), ("axis_method", C.c_int)]
 
 
 class OracleTrace(C.Structure):
@@ -135,8 +135,16 @@ def mufu_rsq(x: np.ndarray) -> np.ndarray:
     return (base.view(np.int32) + mufu_tables()[1][idx].astype(np.int32)).view(np.float32)
 
 
-def make_opt(block_dim=4, has_alpha=False, is_normal_map=False, srgb=False) -> OracleOpt:
-    return OracleOpt(int(block_dim), int(bool(has_alpha)), int(bool(is_normal_map)), int(bool(srgb)))
+def make_opt(block_dim=4, has_alpha=False, is_normal_map=False, srgb=False, axis_method=0) -> OracleOpt:
+    return OracleOpt(int(block_dim), int(bool(has_alpha)), int(bool(is_normal_map)), int(bool(srgb)), int(axis_method))
+
+
+VAR_TRUE_DIVISION, VAR_UNFUSED_SAMPLE, VAR_SRGB_POWF, VAR_EXACT_RCP_RSQ, VAR_UNFUSED_DEV = 1, 2, 4, 8, 16
+
+
+def set_variant(flags: int) -> None:
+    """Sensitivity switches of tools/pin_sensitivity.py (0 = canonical arithmetic).  Process-wide."""
+    lib().astc_oracle_set_variant(int(flags))
 
 
 def num_blocks(width: int, height: int, dim: int) -> tuple[int, int]:
@@ -144,7 +152,7 @@ def num_blocks(width: int, height: int, dim: int) -> tuple[int, int]:
 
 
 def encode_image(rgba: np.ndarray, *, block_dim=4, has_alpha=False, is_normal_map=False,
-                 srgb=False, threads=0) -> np.ndarray:
+                 srgb=False, threads=0, axis_method=0) -> np.ndarray:
     """rgba: (H, W, 4) uint8, row 0 first.  Returns (nblocks, 16) uint8."""
     rgba = np.ascontiguousarray(rgba, dtype=np.uint8)
     h, w, c = rgba.shape
@@ -153,33 +161,33 @@ def encode_image(rgba: np.ndarray, *, block_dim=4, has_alpha=False, is_normal_ma
     out = np.zeros((bw * bh, 16), dtype=np.uint8)
     if bw * bh == 0:
         return out
-    opt = make_opt(block_dim, has_alpha, is_normal_map, srgb)
+    opt = make_opt(block_dim, has_alpha, is_normal_map, srgb, axis_method)
     lib().astc_oracle_encode_image(rgba.ctypes.data, w, h, w * 4, C.byref(opt),
                                    out.ctypes.data, threads)
     return out
 
 
 def encode_rows(rgba: np.ndarray, row0: int, row1: int, *, block_dim=4, has_alpha=False,
-                is_normal_map=False, srgb=False, threads=0) -> tuple[np.ndarray, int]:
+                is_normal_map=False, srgb=False, threads=0, axis_method=0) -> tuple[np.ndarray, int]:
     """Encode block rows [row0,row1) only; returns (blocks, threads_used)."""
     rgba = np.ascontiguousarray(rgba, dtype=np.uint8)
     h, w, _ = rgba.shape
     bw, _bh = num_blocks(w, h, block_dim)
     out = np.zeros((bw * (row1 - row0), 16), dtype=np.uint8)
-    opt = make_opt(block_dim, has_alpha, is_normal_map, srgb)
+    opt = make_opt(block_dim, has_alpha, is_normal_map, srgb, axis_method)
     used = lib().astc_oracle_encode_rows(rgba.ctypes.data, w, h, w * 4, C.byref(opt),
                                          row0, row1, out.ctypes.data, threads)
     return out, used
 
 
 def encode_block(raw: np.ndarray, *, block_dim=4, has_alpha=False, is_normal_map=False,
-                 srgb=False):
+                 srgb=False, axis_method=0):
     """raw: (dim*dim, 4) float32 UNORM values.  Returns (16 bytes, trace)."""
     raw = np.ascontiguousarray(raw, dtype=np.float32)
     assert raw.shape == (block_dim * block_dim, 4)
     out = (C.c_uint8 * 16)()
     tr = OracleTrace()
-    opt = make_opt(block_dim, has_alpha, is_normal_map, srgb)
+    opt = make_opt(block_dim, has_alpha, is_normal_map, srgb, axis_method)
     lib().astc_oracle_encode_block(raw.ctypes.data, C.byref(opt), out, C.byref(tr))
     return np.frombuffer(bytes(out), dtype=np.uint8).copy(), tr
 
