@@ -49,7 +49,7 @@ class AstcError(RuntimeError):
 
 class _Option(C.Structure):
     _fields_ = [("is4x4", C.c_uint8), ("is6x6", C.c_uint8), ("is_normal_map", C.c_uint8),
-                ("has_alpha", C.c_uint8), ("srgb", C.c_uint8), ("reserved", C.c_uint8 * 3)]
+                ("has_alpha", C.c_uint8), ("srgb", C.c_uint8), ("axis_method", C.c_uint8), ("reserved", C.c_uint8 * 2)]
 
 
 class _Image(C.Structure):
@@ -59,16 +59,19 @@ class _Image(C.Structure):
 
 @dataclass
 class encode_option:
-    """Same fields, order and defaults as the reference struct (astc_encode.h:14-28)."""
+    """Same fields, order and defaults as the reference struct (astc_encode.h:14-28), plus one
+    extension: axis_method = 1 selects max_accumulation_pixel_direction (ASTC_Encode.hlsl:170-227,
+    the alternative the reference carries commented out at :514) instead of the PCA (0, default)."""
     is4x4: bool = True
     is6x6: bool = False
     is_normal_map: bool = False
     has_alpha: bool = False
     srgb: bool = False
+    axis_method: int = 0
 
     def _abi(self) -> _Option:
         return _Option(int(self.is4x4), int(self.is6x6), int(self.is_normal_map),
-                       int(self.has_alpha), int(self.srgb))
+                       int(self.has_alpha), int(self.srgb), int(self.axis_method))
 
     @classmethod
     def from_args(cls, args: Sequence[str]) -> "encode_option":
@@ -85,6 +88,8 @@ class encode_option:
                 o.srgb = True
             elif a == "-alpha":
                 o.has_alpha = True
+            elif a == "-accum":                              # extension; the reference ignores unknown flags
+                o.axis_method = 1
         return o
 
 

@@ -59,7 +59,7 @@ uint32_t align_flags(const void *base, size_t pitch)
 // Shared argument validation of every image-shaped entry point.
 int check_image(const void *rgba, int width, int height, size_t pitch, const astc_b200_option *opt, const void *blocks)
 {
-    if (!opt || width < 0 || height < 0) return ASTC_B200_ERR_INVALID_ARGUMENT;
+    if (!opt || width < 0 || height < 0 || opt->axis_method > 1) return ASTC_B200_ERR_INVALID_ARGUMENT;
     if (width == 0 || height == 0) return ASTC_B200_OK;
     if (!rgba || !blocks) return ASTC_B200_ERR_INVALID_ARGUMENT;
     if (pitch < size_t(width) * 4u || pitch % 4u != 0 || reinterpret_cast<uintptr_t>(rgba) % 4u != 0)
@@ -204,7 +204,7 @@ int astc_b200_encode_device(const uint8_t *d_rgba, int width, int height, size_t
     p.table = nullptr;
     p.count = 1;
     p.total_blocks = uint64_t(p.single.blocks_x) * uint64_t((height + d - 1) / d);
-    CUDA_TRY(astc::launch_encode(d, opt->has_alpha != 0, opt->is_normal_map != 0, opt->srgb != 0, p,
+    CUDA_TRY(astc::launch_encode(d, opt->has_alpha != 0, opt->is_normal_map != 0, opt->srgb != 0, opt->axis_method, p,
                                  static_cast<cudaStream_t>(cuda_stream)));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return ASTC_B200_OK;
@@ -213,7 +213,7 @@ int astc_b200_encode_device(const uint8_t *d_rgba, int width, int height, size_t
 int astc_b200_encode_host(const uint8_t *h_rgba, int width, int height, size_t pitch_bytes,
                           const astc_b200_option *opt, uint8_t *h_blocks)
 {
-    if (!opt || width < 0 || height < 0) return ASTC_B200_ERR_INVALID_ARGUMENT;
+    if (!opt || width < 0 || height < 0 || opt->axis_method > 1) return ASTC_B200_ERR_INVALID_ARGUMENT;
     if (width == 0 || height == 0) return ASTC_B200_OK;
     if (!h_rgba || !h_blocks || pitch_bytes < size_t(width) * 4u) return ASTC_B200_ERR_INVALID_ARGUMENT;
     int rc = ensure_pool();
@@ -265,7 +265,7 @@ int astc_b200_encode_host(const uint8_t *h_rgba, int width, int height, size_t p
         p.single = make_desc(d_in + size_t(y0) * d_pitch, d_out + out_off, d_pitch, width, int(y1 - y0), d, 0);
         p.count = 1;
         p.total_blocks = uint64_t(bx) * uint64_t(r1 - r0);
-        err = astc::launch_encode(d, opt->has_alpha != 0, opt->is_normal_map != 0, opt->srgb != 0, p, st);
+        err = astc::launch_encode(d, opt->has_alpha != 0, opt->is_normal_map != 0, opt->srgb != 0, opt->axis_method, p, st);
         if (err != cudaSuccess) break;
         g_launches.fetch_add(1, std::memory_order_relaxed);
         err = cudaMemcpyAsync(h_blocks + out_off, d_out + out_off, out_bytes, cudaMemcpyDeviceToHost, st);
@@ -327,7 +327,7 @@ int astc_b200_batch_encode(astc_b200_batch *batch, void *cuda_stream)
     p.count = int(batch->host.size());
     p.total_blocks = batch->blocks;
     CUDA_TRY(astc::launch_encode(dim_of(&batch->opt), batch->opt.has_alpha != 0, batch->opt.is_normal_map != 0,
-                                 batch->opt.srgb != 0, p, static_cast<cudaStream_t>(cuda_stream)));
+                                 batch->opt.srgb != 0, batch->opt.axis_method, p, static_cast<cudaStream_t>(cuda_stream)));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return ASTC_B200_OK;
 }

@@ -1,7 +1,9 @@
 // astc_cs_enc -- command-line front end with the reference's surface
 // (main.cpp:140-258, README.md:27-40):
 //
-//     astc_cs_enc <input image> [-4x4] [-6x6] [-alpha] [-norm] [-srgb]
+//     astc_cs_enc <input image> [-4x4] [-6x6] [-alpha] [-norm] [-srgb] [-accum]
+//
+// (-accum is an extension: max_accumulation_pixel_direction, ASTC_Encode.hlsl:170-227, instead of the PCA.)
 //
 // Same flag spelling and semantics (flags are read from argv[2] on, unknown
 // flags are ignored), same stdout lines, same output naming (<input minus its
@@ -70,6 +72,7 @@ static bool parse_cmd(int argc, char **argv, encode_option &option)
         else if (arg == "-norm") target = &option.is_normal_map;
         else if (arg == "-srgb") target = &option.srgb;
         else if (arg == "-alpha") target = &option.has_alpha;
+        else if (arg == "-accum") target = &option.max_accumulation_axis;   // extension: the reference's commented-out axis heuristic
         if (target) *target = true;
     }
     return true;

@@ -282,7 +282,7 @@ __device__ __forceinline__ bool prefetch_rows4x4(const EncodeParams &p, const Wa
 #ifndef ASTC_MINBLOCKS_4X4_NORMAL
 #define ASTC_MINBLOCKS_4X4_NORMAL 7
 #endif
-template <bool ALPHA, bool NORMAL, bool SRGB, bool BATCH>
+template <bool ALPHA, bool NORMAL, bool SRGB, bool BATCH, bool ACCUM>
 __global__ void __launch_bounds__(kThreads4x4, NORMAL ? ASTC_MINBLOCKS_4X4_NORMAL : ASTC_MINBLOCKS_4X4)
 encode4x4_kernel(const EncodeParams p)
 {
@@ -334,7 +334,7 @@ encode4x4_kernel(const EncodeParams p)
         const bool more = pass + 1 < p.passes && wk.advance(p, kThreads4x4);
         if (more) fast = prefetch_rows4x4<BATCH>(p, wk, slot0 + uint32_t((pass + 1) & 1) * kSlotStride);
         // one coalesced 16-byte store per thread
-        *out = dev::encode_block<4, ALPHA, NORMAL>(tx, sum_lo, sum_hi, s_field, s_trit);
+        *out = dev::encode_block<4, ALPHA, NORMAL, ACCUM>(tx, sum_lo, sum_hi, s_field, s_trit);
         if (!more) break;
     }
 }
@@ -399,7 +399,7 @@ constexpr size_t smem6x6()
 template <bool NORMAL>
 constexpr int ctas6x6() { return NORMAL ? 6 : 4; }
 
-template <bool ALPHA, bool NORMAL, bool SRGB, bool BATCH>
+template <bool ALPHA, bool NORMAL, bool SRGB, bool BATCH, bool ACCUM>
 __global__ void __launch_bounds__(kThreads6x6, ctas6x6<NORMAL>())
 encode6x6_kernel(const EncodeParams p)
 {
@@ -463,7 +463,7 @@ encode6x6_kernel(const EncodeParams p)
         }
         if (NORMAL) sum_hi = dev::bc(36.0f * 255.0f);
         tx.fence();                                        // no store-to-load forwarding: the passes stream from shared memory
-        *wk.out(p) = dev::encode_block<6, ALPHA, NORMAL>(tx, sum_lo, sum_hi, s_field, s_trit);
+        *wk.out(p) = dev::encode_block<6, ALPHA, NORMAL, ACCUM>(tx, sum_lo, sum_hi, s_field, s_trit);
         if (pass + 1 >= p.passes || !wk.advance(p, kThreads6x6)) break;
     }
 }
@@ -494,7 +494,7 @@ static int choose_passes(uint64_t total_blocks, int threads, int ctas_per_sm, in
     return want < 1 ? 1 : want > uint64_t(max_passes) ? max_passes : int(want);
 }
 
-template <bool ALPHA, bool NORMAL, bool SRGB, bool BATCH>
+template <bool ALPHA, bool NORMAL, bool SRGB, bool BATCH, bool ACCUM>
 static cudaError_t launch_variant(int dim, EncodeParams p, cudaStream_t stream)
 {
     if (dim == 4) {
@@ -502,9 +502,9 @@ static cudaError_t launch_variant(int dim, EncodeParams p, cudaStream_t stream)
         const uint64_t per_cta = uint64_t(kThreads4x4) * uint64_t(p.passes);
         const uint64_t ctas = (p.total_blocks + per_cta - 1) / per_cta;
         if (ctas > 0x7FFFFFFFull) return cudaErrorInvalidConfiguration;
-        encode4x4_kernel<ALPHA, NORMAL, SRGB, BATCH><<<unsigned(ctas), kThreads4x4, 0, stream>>>(p);
+        encode4x4_kernel<ALPHA, NORMAL, SRGB, BATCH, ACCUM><<<unsigned(ctas), kThreads4x4, 0, stream>>>(p);
     } else {
-        auto kern = encode6x6_kernel<ALPHA, NORMAL, SRGB, BATCH>;
+        auto kern = encode6x6_kernel<ALPHA, NORMAL, SRGB, BATCH, ACCUM>;
         constexpr size_t kSmem6x6 = smem6x6<NORMAL>();
         constexpr int kCtas6x6 = ctas6x6<NORMAL>();
         p.passes = choose_passes(p.total_blocks, kThreads6x6, kCtas6x6, 2);
@@ -524,7 +524,7 @@ static cudaError_t launch_variant(int dim, EncodeParams p, cudaStream_t stream)
     return cudaGetLastError();
 }
 
-template <bool BATCH>
+template <bool BATCH, bool ACCUM>
 static cudaError_t dispatch(int dim, bool alpha, bool normal, bool srgb, const EncodeParams &p, cudaStream_t s)
 {
     // IS_NORMALMAP / HAS_ALPHA macros of astc_encode.h:55-62 become template
@@ -532,21 +532,23 @@ static cudaError_t dispatch(int dim, bool alpha, bool normal, bool srgb, const E
     if (normal) srgb = false;
     const int key = (alpha ? 4 : 0) | (normal ? 2 : 0) | (srgb ? 1 : 0);
     switch (key) {
-    case 0: return launch_variant<false, false, false, BATCH>(dim, p, s);
-    case 1: return launch_variant<false, false, true, BATCH>(dim, p, s);
-    case 2: return launch_variant<false, true, false, BATCH>(dim, p, s);
-    case 4: return launch_variant<true, false, false, BATCH>(dim, p, s);
-    case 5: return launch_variant<true, false, true, BATCH>(dim, p, s);
-    case 6: return launch_variant<true, true, false, BATCH>(dim, p, s);
+    case 0: return launch_variant<false, false, false, BATCH, ACCUM>(dim, p, s);
+    case 1: return launch_variant<false, false, true, BATCH, ACCUM>(dim, p, s);
+    case 2: return launch_variant<false, true, false, BATCH, ACCUM>(dim, p, s);
+    case 4: return launch_variant<true, false, false, BATCH, ACCUM>(dim, p, s);
+    case 5: return launch_variant<true, false, true, BATCH, ACCUM>(dim, p, s);
+    case 6: return launch_variant<true, true, false, BATCH, ACCUM>(dim, p, s);
     default: return cudaErrorInvalidValue;
     }
 }
 
-cudaError_t launch_encode(int dim, bool alpha, bool normal, bool srgb, const EncodeParams &p, cudaStream_t stream)
+cudaError_t launch_encode(int dim, bool alpha, bool normal, bool srgb, int axis_method, const EncodeParams &p, cudaStream_t stream)
 {
     if (p.total_blocks == 0) return cudaSuccess;
-    return p.count > 1 || p.table != nullptr ? dispatch<true>(dim, alpha, normal, srgb, p, stream)
-                                             : dispatch<false>(dim, alpha, normal, srgb, p, stream);
+    const bool batch = p.count > 1 || p.table != nullptr;
+    if (axis_method == 1)
+        return batch ? dispatch<true, true>(dim, alpha, normal, srgb, p, stream) : dispatch<false, true>(dim, alpha, normal, srgb, p, stream);
+    return batch ? dispatch<true, false>(dim, alpha, normal, srgb, p, stream) : dispatch<false, false>(dim, alpha, normal, srgb, p, stream);
 }
 
 // ---------------------------------------------------------------------------

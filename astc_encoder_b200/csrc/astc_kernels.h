@@ -32,7 +32,8 @@ struct EncodeParams {
     int32_t passes;              // blocks each thread encodes one after the other (set by launch_encode)
 };
 
-cudaError_t launch_encode(int dim, bool alpha, bool normal, bool srgb, const EncodeParams &p, cudaStream_t stream);
+// axis_method: 0 = PCA power iteration (the reference's shipped path), 1 = max_accumulation_pixel_direction
+cudaError_t launch_encode(int dim, bool alpha, bool normal, bool srgb, int axis_method, const EncodeParams &p, cudaStream_t stream);
 cudaError_t launch_bise(const uint8_t *d_values, int count, int quant, int nseq, uint8_t *d_streams, cudaStream_t stream);
 cudaError_t launch_decode(const uint8_t *d_blocks, int width, int height, int dim, uint8_t *d_rgba, size_t pitch,
                           cudaStream_t stream);

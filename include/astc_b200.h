@@ -62,7 +62,12 @@ typedef struct astc_b200_option {
     uint8_t is_normal_map;
     uint8_t has_alpha;
     uint8_t srgb;
-    uint8_t reserved[3];
+    /* Extension (not a field of the reference struct; 0 keeps the reference's behaviour): which of the
+     * two axis heuristics of ASTC_Encode.hlsl picks the endpoint direction.
+     *   0  principal_component_analysis  (:139-168, called at :515 -- what the reference ships)
+     *   1  max_accumulation_pixel_direction (:170-227, its call is commented out at :514)           */
+    uint8_t axis_method;
+    uint8_t reserved[2];
 } astc_b200_option;
 
 /* One texture of a batch (mip level, array slice ...). All device pointers. */

@@ -20,6 +20,10 @@ struct encode_option {
     bool is_normal_map = false;
     bool has_alpha = false;
     bool srgb = false;
+    // Extension (after the reference's fields, so aggregate use of the first five is unchanged): the axis
+    // heuristic.  false = principal_component_analysis (ASTC_Encode.hlsl:515, what the reference ships);
+    // true = max_accumulation_pixel_direction (:170-227, its call is commented out at :514).  CLI: -accum.
+    bool max_accumulation_axis = false;
 };
 
 // Block edge for an option set.  The reference derives it from is4x4 alone
@@ -36,6 +40,7 @@ inline astc_b200_option to_abi(const encode_option &option, bool srgb_texture)
     o.is_normal_map = option.is_normal_map;
     o.has_alpha = option.has_alpha;
     o.srgb = srgb_texture;          // the sRGB decode belongs to the texture format (main.cpp:38,214)
+    o.axis_method = option.max_accumulation_axis ? 1 : 0;
     return o;
 }
 

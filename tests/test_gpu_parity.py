@@ -105,3 +105,43 @@ def test_mixed_content_all_variants(native, oracle, dim, seed):
         got = _gpu_encode(native, img, _opt(native, dim, v))
         want = oracle.encode_image(img, block_dim=dim, **v)
         assert got.shape == want.shape and np.array_equal(got, want), ((w, h), v, _mismatch_report(got, want))
+
+
+@pytest.mark.parametrize("dim", [4, 6])
+@pytest.mark.parametrize("kw", [dict(), dict(has_alpha=True), dict(srgb=True), dict(has_alpha=True, srgb=True),
+                                dict(is_normal_map=True)], ids=str)
+def test_max_accumulation_axis_matches_oracle(native, oracle, dim, kw):
+    """axis_method = 1 (max_accumulation_pixel_direction, ASTC_Encode.hlsl:170-227, opt-in): the kernel
+    variant against the oracle's restatement, bit-exact, aligned and ragged sizes, synthetic + leaf-like content."""
+    import torch
+    from astc_encoder_b200 import synth
+    opt = native.encode_option(is4x4=dim == 4, is6x6=dim == 6, axis_method=1, **kw)
+    for (w, h, seed) in ((512, 384, 21), (250, 187, 22), (7, 5, 23)):
+        img = (synth.synth_normal if kw.get("is_normal_map") else synth.synth_rgba)(w, h, seed)
+        got = native.read_gpu(native.encode_astc(img.cuda(), opt))
+        want = oracle.encode_image(img.numpy(), block_dim=dim, axis_method=1, **kw)
+        bad = np.nonzero((got != want).any(axis=1))[0]
+        assert len(bad) == 0, (dim, kw, w, h, bad[:8])
+    # special content: flat, two-tone, alpha-only variation
+    rng = np.random.default_rng(3)
+    n = 48
+    flat = np.repeat(rng.integers(0, 256, (1, n, 1, 4), dtype=np.uint8), dim, axis=2).reshape(1, n * dim, 4).repeat(dim, 0)
+    aonly = flat.copy(); aonly[..., 3] = rng.integers(0, 256, (dim, n * dim))
+    two = np.where(rng.random((dim, n * dim, 1)) < 0.5, rng.integers(0, 256, 4), rng.integers(0, 256, 4)).astype(np.uint8)
+    img = np.ascontiguousarray(np.concatenate([flat, aonly, two], axis=0))
+    got = native.read_gpu(native.encode_astc(torch.from_numpy(img).cuda(), opt))
+    want = oracle.encode_image(img, block_dim=dim, axis_method=1, **kw)
+    assert np.array_equal(got, want)
+
+
+def test_max_accumulation_axis_in_a_batch(native, oracle):
+    import torch
+    from astc_encoder_b200 import synth
+    opt = native.encode_option(has_alpha=True, axis_method=1)
+    chain = native.mip_chain(synth.synth_rgba(128, 64, 31).cuda())
+    batch = native.Batch(chain, opt)
+    outs = batch.encode()
+    torch.cuda.synchronize()
+    for lvl, o in zip(chain, outs):
+        assert np.array_equal(o.cpu().numpy(), oracle.encode_image(lvl.cpu().numpy(), block_dim=4, has_alpha=True, axis_method=1))
+    batch.close()

@@ -118,3 +118,23 @@ def test_mufu_tables_and_emulation(oracle):
     assert np.array_equal(oracle.mufu_rsq(xs), np.array([L.astc_oracle_mufu_rsq(float(x)) for x in xs], np.float32))
     # within 2 ulp of the correctly rounded values
     assert np.max(np.abs(oracle.mufu_rsq(xs).view(np.int32) - (1.0 / np.sqrt(xs.astype(np.float64))).astype(np.float32).view(np.int32))) <= 2
+
+
+def test_residual_blocks_are_the_committed_list(oracle, encoded, leaf_golden):
+    """The 39 golden blocks the canonical arithmetic does not reproduce are listed, with their class and
+    their distance to the rounding decision they sit on, in tests/golden/leaf_residual_blocks.json
+    (tools/golden_residual.py).  The oracle must differ from the golden in exactly those blocks."""
+    import json
+    listed = json.loads((GOLDEN / "leaf_residual_blocks.json").read_text())
+    bad = np.nonzero((encoded != leaf_golden[4]).any(axis=1))[0]
+    assert [r["block"] for r in listed["blocks"]] == bad.tolist()
+    assert listed["identical"] == 65536 - len(bad) == 65497
+    by_class = {}
+    for r in listed["blocks"]:
+        by_class.setdefault(r["class"], []).append(r)
+    assert {k: len(v) for k, v in by_class.items()} == {"weights+-1": 25, "endpoint_swap_tie": 5, "endpoint_lsb": 4, "axis_divergence": 5}
+    # weights+-1: one quantisation step, and (23 of 25) a weight within an ulp of k + 0.5 in OUR arithmetic too
+    assert all(r["max_weight_step"] == 1 and r["max_endpoint_delta"] == 0 for r in by_class["weights+-1"])
+    assert sum(r["closest_weight_to_a_half"] <= 3e-7 for r in by_class["weights+-1"]) >= 23
+    # swap ties: the rounded rgb sums of the two endpoints are EQUAL here, so `>` (:127) hangs on the last bit
+    assert all(r["rounded_rgb_sum_e1_minus_e0"] == 0.0 for r in by_class["endpoint_swap_tie"])

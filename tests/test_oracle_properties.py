@@ -112,3 +112,26 @@ def test_normal_map_ignores_srgb_and_blue_alpha(oracle):
 
 def test_empty_image(oracle):
     assert oracle.encode_image(np.zeros((0, 16, 4), np.uint8)).shape == (0, 16)
+
+
+def test_max_accumulation_axis_oracle_properties(oracle):
+    """max_accumulation_pixel_direction (ASTC_Encode.hlsl:170-227) in the oracle: valid blocks, ordered endpoints,
+    flat blocks identical to the PCA path, and on a block varying along ONE channel the same endpoints as the PCA."""
+    rng = np.random.default_rng(12)
+    img = rng.integers(0, 256, (64, 64, 4), dtype=np.uint8)
+    for dim in (4, 6):
+        for kw in (dict(), dict(has_alpha=True), dict(is_normal_map=True)):
+            enc = oracle.encode_image(img, block_dim=dim, axis_method=1, **kw)
+            sym = oracle.unpack_blocks(enc)
+            assert sym["ok"].all()
+            ep = sym["ep"].astype(int)
+            assert np.all(ep[:, 0] + ep[:, 2] + ep[:, 4] <= ep[:, 1] + ep[:, 3] + ep[:, 5])     # no blue contraction on decode
+            dec, bad = oracle.decode_image(enc, 64, 64, dim)
+            assert bad == 0
+    flat = np.full((8, 8, 4), 77, np.uint8)
+    assert np.array_equal(oracle.encode_image(flat, block_dim=4, has_alpha=True, axis_method=1),
+                          oracle.encode_image(flat, block_dim=4, has_alpha=True))
+    ramp = np.zeros((4, 4, 4), np.uint8); ramp[..., 3] = 255; ramp[..., 1] = (np.arange(16).reshape(4, 4) * 9 + 20)
+    a = oracle.unpack_blocks(oracle.encode_image(ramp, block_dim=4, axis_method=1))
+    b = oracle.unpack_blocks(oracle.encode_image(ramp, block_dim=4))
+    assert np.array_equal(a["ep"], b["ep"])

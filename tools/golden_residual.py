@@ -1,0 +1,78 @@
+#!/usr/bin/env python3
+"""Which blocks of the reference's golden (textures/leaf.astc) does the canonical arithmetic NOT
+reproduce, and how far off is each?  Writes tests/golden/leaf_residual_blocks.json (the list
+tests/test_oracle_golden.py pins) and prints a summary.
+
+Classes:
+  weights+-1            endpoints identical; n weights differ, each by exactly one QUANT_6 step: a projected
+                        weight landed within rounding distance of k + 0.5 and the golden's GPU rounded the other way
+  endpoint_swap_tie     e0 <-> e1 exchanged and the weights mirrored (5 - q): the rounded rgb sums of the two
+                        endpoints tie or differ in the last bit, so `e0u.xyz sum > e1u.xyz sum` (:127) flips
+  endpoint_lsb          some endpoint byte differs by 1 (a clamp(k*t+mean) value within rounding distance of .5),
+                        weights follow within +-1
+  axis_divergence       endpoint bytes differ by more than 1: the power iteration amplified a last-bit difference
+                        (near-degenerate covariance: two eigenvalues close, the seed decides)
+    python tools/golden_residual.py        (CPU only: oracle + PIL)
+"""
+import json
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+from oracle import oracle as O                                    # noqa: E402
+
+
+def main():
+    from PIL import Image
+    img = np.ascontiguousarray(np.asarray(Image.open(ROOT / "tests/golden/leaf.png").convert("RGBA"))[::-1])
+    gold = np.frombuffer((ROOT / "tests/golden/leaf.astc").read_bytes()[16:], np.uint8).reshape(-1, 16)
+    enc = O.encode_image(img, block_dim=4, has_alpha=True)
+    bad = np.nonzero((enc != gold).any(axis=1))[0]
+    a, g = O.unpack_blocks(enc[bad]), O.unpack_blocks(gold[bad])
+    rows = []
+    lut = O.unorm_lut(False)
+    for i, b in enumerate(bad):
+        bx, by = int(b % 256), int(b // 256)
+        _, tr = O.encode_block(lut[img[by * 4:by * 4 + 4, bx * 4:bx * 4 + 4].reshape(16, 4)], block_dim=4, has_alpha=True)
+        q = np.array(tr.projw[:], np.float64) * 5.0                # what round() is applied to (:256-260)
+        e0, e1 = np.array(tr.e0[:], np.float64), np.array(tr.e1[:], np.float64)
+        ea, eg = a["ep"][i].astype(int), g["ep"][i].astype(int)
+        wa, wg = a["weights"][i].astype(int), g["weights"][i].astype(int)
+        dep = np.abs(ea - eg)
+        swapped = np.array_equal(ea[0::2], eg[1::2]) and np.array_equal(ea[1::2], eg[0::2])
+        if not dep.any():
+            cls = "weights+-1"
+        elif swapped and np.array_equal(wa, 5 - wg):
+            cls = "endpoint_swap_tie"
+        elif dep.max() <= 1:
+            cls = "endpoint_lsb"
+        else:
+            cls = "axis_divergence"
+        differing = np.nonzero(wa != wg)[0]
+        tie = np.abs((q[differing] - np.floor(q[differing])) - 0.5) if len(differing) else np.zeros(0)
+        rows.append({"block": int(b), "bx": bx, "by": by, "class": cls,
+                     "weights_differing": int((wa != wg).sum()), "max_weight_step": int(np.abs(wa - wg).max()),
+                     "max_endpoint_delta": int(dep.max()),
+                     # how close our own numbers are to the decision boundary the golden fell on the other side of
+                     "closest_weight_to_a_half": (float(f"{tie.min():.3g}") if len(tie) else None),
+                     "rounded_rgb_sum_e1_minus_e0": float(np.rint(e1[:3]).sum() - np.rint(e0[:3]).sum()),
+                     "closest_endpoint_to_a_half": float(f"{np.abs((np.concatenate([e0, e1]) % 1.0) - 0.5).min():.3g}"),
+                     "endpoints_ours": ea.tolist(), "endpoints_golden": eg.tolist()})
+    out = {"golden": "textures/leaf.astc (reference), 65536 blocks, encoded -alpha -4x4 from the flipped leaf.png",
+           "arithmetic": "canonical (DESIGN.md 2): FMA contraction as listed, MUFU rcp / rsq",
+           "identical": int(len(gold) - len(bad)), "different": int(len(bad)), "blocks": rows}
+    (ROOT / "tests/golden/leaf_residual_blocks.json").write_text(json.dumps(out, indent=1) + "\n")
+    from collections import Counter
+    c = Counter(r["class"] for r in rows)
+    print(f"{len(gold) - len(bad)} of {len(gold)} blocks identical; {len(bad)} differ: {dict(c)}")
+    for r in rows:
+        print(f"  block {r['block']:6d} ({r['bx']:3d},{r['by']:3d}) {r['class']:18s} weights differing {r['weights_differing']:2d} (max step {r['max_weight_step']})"
+              f"  max endpoint delta {r['max_endpoint_delta']}")
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
