@@ -26,7 +26,7 @@ import numpy as np
 __all__ = [
     "encode_option", "AstcError", "lib", "block_dim", "block_counts", "output_size", "band",
     "encode_astc", "encode_astc_host", "read_gpu", "save_astc", "save_astc_slice", "load_astc", "load_image", "load_tex",
-    "decode_astc", "downsample2x2", "mip_chain", "mufu", "bise_encode", "Batch", "launch_count", "unorm_lut", "version",
+    "decode_astc", "downsample2x2", "mip_chain", "mufu", "bise_encode", "Batch", "Context", "launch_count", "unorm_lut", "version",
 ]
 
 _PKG = Path(__file__).resolve().parent
@@ -50,6 +50,11 @@ class AstcError(RuntimeError):
 class _Option(C.Structure):
     _fields_ = [("is4x4", C.c_uint8), ("is6x6", C.c_uint8), ("is_normal_map", C.c_uint8),
                 ("has_alpha", C.c_uint8), ("srgb", C.c_uint8), ("axis_method", C.c_uint8), ("reserved", C.c_uint8 * 2)]
+
+
+class _HostImage(C.Structure):
+    _fields_ = [("h_rgba", C.c_void_p), ("h_blocks", C.c_void_p), ("pitch_bytes", C.c_size_t),
+                ("width", C.c_int32), ("height", C.c_int32)]
 
 
 class _Image(C.Structure):
@@ -112,6 +117,11 @@ _SIGNATURES = {
                                  C.POINTER(C.c_int), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "astc_b200_encode_device": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.POINTER(_Option), C.c_void_p, C.c_void_p]),
     "astc_b200_encode_host": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.POINTER(_Option), C.c_void_p]),
+    "astc_b200_context_create": (C.c_int, [C.POINTER(C.c_void_p)]),
+    "astc_b200_context_destroy": (None, [C.c_void_p]),
+    "astc_b200_context_trim": (C.c_int, [C.c_void_p]),
+    "astc_b200_context_encode_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.POINTER(_Option), C.c_void_p]),
+    "astc_b200_context_batch_encode_host": (C.c_int, [C.c_void_p, C.POINTER(_HostImage), C.c_int, C.POINTER(_Option)]),
     "astc_b200_batch_create": (C.c_int, [C.POINTER(_Image), C.c_int, C.POINTER(_Option), C.POINTER(C.c_void_p)]),
     "astc_b200_batch_encode": (C.c_int, [C.c_void_p, C.c_void_p]),
     "astc_b200_batch_total_blocks": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
@@ -248,6 +258,13 @@ def encode_astc_host(rgba: np.ndarray, option: encode_option, out: Optional[np.n
                      srgb_texture: Optional[bool] = None) -> np.ndarray:
     """Upload + encode + read-back in one synchronous call on host memory
     (load_tex's upload + encode_astc + read_gpu).  rgba: (H, W, 4) uint8."""
+    rgba, o, out, pitch = _host_args(rgba, option, out, srgb_texture)
+    h, w = rgba.shape[:2]
+    _check(lib().astc_b200_encode_host(rgba.ctypes.data, w, h, pitch, C.byref(o), out.ctypes.data), "encode_astc_host")
+    return out
+
+
+def _host_args(rgba, option, out, srgb_texture):
     if rgba.dtype != np.uint8 or rgba.ndim != 3 or rgba.shape[2] != 4 or \
             (rgba.size and (rgba.strides[2] != 1 or rgba.strides[1] != 4)):
         raise ValueError("rgba must be a uint8 array of shape (H, W, 4) with packed texels")
@@ -256,9 +273,59 @@ def encode_astc_host(rgba: np.ndarray, option: encode_option, out: Optional[np.n
     nbytes = int(lib().astc_b200_output_size(w, h, C.byref(o)))
     if out is None:
         out = np.empty((nbytes // BLOCK_BYTES, BLOCK_BYTES), dtype=np.uint8)
+    elif out.dtype != np.uint8 or not out.flags.c_contiguous or out.size < nbytes:
+        raise ValueError("out must be a contiguous uint8 array of at least output_size bytes")
     pitch = rgba.strides[0] if (h > 1 and rgba.size) else w * 4
-    _check(lib().astc_b200_encode_host(rgba.ctypes.data, w, h, pitch, C.byref(o), out.ctypes.data), "encode_astc_host")
-    return out
+    return rgba, o, out, pitch
+
+
+class Context:
+    """Persistent host-side context (astc_b200_context_*): streams, device workspace and pinned staging
+    kept across calls.  One per (host thread, device); create it with the target device current."""
+
+    def __init__(self):
+        self._h = C.c_void_p()
+        _check(lib().astc_b200_context_create(C.byref(self._h)), "Context")
+
+    def encode_host(self, rgba: np.ndarray, option: encode_option, out: Optional[np.ndarray] = None,
+                    srgb_texture: Optional[bool] = None) -> np.ndarray:
+        rgba, o, out, pitch = _host_args(rgba, option, out, srgb_texture)
+        h, w = rgba.shape[:2]
+        _check(lib().astc_b200_context_encode_host(self._h, rgba.ctypes.data, w, h, pitch, C.byref(o), out.ctypes.data),
+               "Context.encode_host")
+        return out
+
+    def batch_encode_host(self, images: Sequence[np.ndarray], option: encode_option,
+                          outs: Optional[Sequence[np.ndarray]] = None) -> list:
+        """Many (H, W, 4) uint8 host images -> list of (blocks, 16) uint8 arrays, one synchronous call."""
+        o = option._abi()
+        imgs, res = (_HostImage * max(1, len(images)))(), []
+        for i, im in enumerate(images):
+            if im.dtype != np.uint8 or im.ndim != 3 or im.shape[2] != 4 or (im.size and (im.strides[2] != 1 or im.strides[1] != 4)):
+                raise ValueError("images must be uint8 arrays of shape (H, W, 4) with packed texels")
+            h, w = im.shape[:2]
+            n = int(lib().astc_b200_output_size(w, h, C.byref(o)))
+            dst = outs[i] if outs is not None else np.empty((n // BLOCK_BYTES, BLOCK_BYTES), dtype=np.uint8)
+            if dst.dtype != np.uint8 or not dst.flags.c_contiguous or dst.size < n:
+                raise ValueError("outs[i] must be a contiguous uint8 array of at least output_size bytes")
+            res.append(dst)
+            imgs[i] = _HostImage(im.ctypes.data, dst.ctypes.data, im.strides[0] if (h > 1 and im.size) else w * 4, w, h)
+        _check(lib().astc_b200_context_batch_encode_host(self._h, imgs, len(images), C.byref(o)), "Context.batch_encode_host")
+        return res
+
+    def trim(self) -> None:
+        _check(lib().astc_b200_context_trim(self._h), "Context.trim")
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            lib().astc_b200_context_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def read_gpu(buffer, stream=None) -> np.ndarray:

@@ -18,6 +18,7 @@ CSRC = PKG / "csrc"
 INCLUDE = PKG.parent / "include"
 LIB = PKG / "libastc_b200.so"
 CLI = PKG / "bin" / "astc_cs_enc"
+SOURCES = ("astc_kernels.cu", "astc_capi.cu", "astc_context.cu", "image_io.cpp")
 
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -63,16 +64,20 @@ def build_variant(tag: str, defines, verbose: bool = False) -> Path:
     objdir = PKG / "_obj"
     objdir.mkdir(exist_ok=True)
     lib = PKG / f"libastc_b200_{tag}.so"
-    kobj = objdir / f"astc_kernels_{tag}.o"
-    _run([nvcc, "-ccbin", _host_cxx(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", CSRC / "astc_kernels.cu", "-o", kobj], verbose)
-    objs = [kobj]
-    for src in ("astc_capi.cu", "image_io.cpp"):
-        obj = objdir / (src.rsplit(".", 1)[0] + ".o")
-        if not obj.exists():
-            _run([nvcc, "-ccbin", _host_cxx(), *NVCC_FLAGS, "-c", CSRC / src, "-o", obj], verbose)
+    objs = []
+    for src in SOURCES:
+        if src.endswith(".cu"):                              # the CUDA translation units see the experiment's defines
+            obj = objdir / f"{src.rsplit('.', 1)[0]}_{tag}.o"
+            _run([nvcc, "-ccbin", _host_cxx(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", CSRC / src, "-o", obj], verbose)
+        else:
+            obj = objdir / (src.rsplit(".", 1)[0] + ".o")
+            if not obj.exists():
+                _run([nvcc, "-ccbin", _host_cxx(), *NVCC_FLAGS, "-c", CSRC / src, "-o", obj], verbose)
         objs.append(obj)
     _run([nvcc, "-ccbin", _host_cxx(), "-shared", "-o", lib, *objs, "-lz"], verbose)
-    kobj.unlink()
+    for obj in objs:
+        if obj.name.endswith(f"_{tag}.o"):
+            obj.unlink()
     return lib
 
 
@@ -84,7 +89,7 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
     if force or _stale(LIB, deps):
         objdir.mkdir(exist_ok=True)
         objs = []
-        for src in ("astc_kernels.cu", "astc_capi.cu", "image_io.cpp"):
+        for src in SOURCES:
             obj = objdir / (src.rsplit(".", 1)[0] + ".o")
             if force or _stale(obj, deps):
                 extra = ["-Xptxas", "-v"] if (ptxas_info and src.endswith(".cu")) else []

@@ -22,15 +22,17 @@
 #include <string>
 #include <vector>
 
+#include "astc_capi_internal.h"
 #include "astc_kernels.h"
 #include "astc_tables.h"
 #include "astc_save.h"
 
 namespace {
-
 thread_local std::string g_last_cuda_error;
 std::atomic<uint64_t> g_launches{0};
+}  // namespace
 
+namespace astc_capi {
 int cuda_fail(cudaError_t e, const char *what)
 {
     g_last_cuda_error = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
@@ -38,23 +40,14 @@ int cuda_fail(cudaError_t e, const char *what)
     if (e == cudaErrorMemoryAllocation) return ASTC_B200_ERR_OUT_OF_MEMORY;
     return ASTC_B200_ERR_CUDA;
 }
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+}  // namespace astc_capi
 
-#define CUDA_TRY(expr)                                           \
-    do {                                                         \
-        cudaError_t e__ = (expr);                                \
-        if (e__ != cudaSuccess) return cuda_fail(e__, #expr);    \
-    } while (0)
+using astc_capi::cuda_fail;
+using astc_capi::dim_of;
+using astc_capi::make_desc;
 
-int dim_of(const astc_b200_option *o) { return (o->is6x6 || !o->is4x4) ? 6 : 4; }
-
-uint32_t align_flags(const void *base, size_t pitch)
-{
-    const uintptr_t b = reinterpret_cast<uintptr_t>(base);
-    uint32_t f = 0;
-    if (b % 16 == 0 && pitch % 16 == 0) f |= astc::kFlagAligned16;
-    if (b % 8 == 0 && pitch % 8 == 0) f |= astc::kFlagAligned8;
-    return f;
-}
+namespace {
 
 // Shared argument validation of every image-shaped entry point.
 int check_image(const void *rgba, int width, int height, size_t pitch, const astc_b200_option *opt, const void *blocks)
@@ -65,31 +58,6 @@ int check_image(const void *rgba, int width, int height, size_t pitch, const ast
     if (pitch < size_t(width) * 4u || pitch % 4u != 0 || reinterpret_cast<uintptr_t>(rgba) % 4u != 0)
         return ASTC_B200_ERR_INVALID_ARGUMENT;
     if (reinterpret_cast<uintptr_t>(blocks) % 16u != 0) return ASTC_B200_ERR_INVALID_ARGUMENT;
-    return ASTC_B200_OK;
-}
-
-astc::ImageDesc make_desc(const uint8_t *rgba, uint8_t *blocks, size_t pitch, int w, int h, int dim, uint64_t first)
-{
-    astc::ImageDesc d{};
-    d.rgba = rgba; d.blocks = blocks; d.pitch = pitch; d.first_block = first;
-    d.width = w; d.height = h;
-    d.blocks_x = uint32_t((w + dim - 1) / dim);
-    d.flags = align_flags(rgba, pitch);
-    return d;
-}
-
-int ensure_pool()
-{
-    // keep freed workspace in the stream-ordered pool instead of returning it to the driver
-    static thread_local int configured = -1;
-    int dev = 0;
-    CUDA_TRY(cudaGetDevice(&dev));
-    if (configured == dev) return ASTC_B200_OK;
-    cudaMemPool_t pool;
-    CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, dev));
-    uint64_t keep = ~0ull;
-    CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-    configured = dev;
     return ASTC_B200_OK;
 }
 
@@ -210,79 +178,6 @@ int astc_b200_encode_device(const uint8_t *d_rgba, int width, int height, size_t
     return ASTC_B200_OK;
 }
 
-int astc_b200_encode_host(const uint8_t *h_rgba, int width, int height, size_t pitch_bytes,
-                          const astc_b200_option *opt, uint8_t *h_blocks)
-{
-    if (!opt || width < 0 || height < 0 || opt->axis_method > 1) return ASTC_B200_ERR_INVALID_ARGUMENT;
-    if (width == 0 || height == 0) return ASTC_B200_OK;
-    if (!h_rgba || !h_blocks || pitch_bytes < size_t(width) * 4u) return ASTC_B200_ERR_INVALID_ARGUMENT;
-    int rc = ensure_pool();
-    if (rc != ASTC_B200_OK) return rc;
-
-    const int d = dim_of(opt);
-    const int64_t bx = (width + d - 1) / d, by = (height + d - 1) / d;
-    const size_t d_pitch = (size_t(width) * 4u + 127u) & ~size_t(127);
-    // Bands keep the three engines (H2D, SM, D2H) busy at once.  The H2D copies are the bottleneck and
-    // run back to back; what the banding costs on top is the drain after the last copy (that band's
-    // kernel and its D2H: ~5.2 ps per byte of band) plus ~7.8 us of launch / copy overhead per band
-    // (both measured on B200 / PCIe Gen5: 1 GiB in 1 / 8 / 32 / 128 MiB bands = 28.4 / 20.8 / 20.45 /
-    // 20.9 ms).  The sum is smallest at sqrt(5.2e-12 / 7.8e-6 * bytes) bands: 27 for 1 GiB, 7 for 64 MiB.
-    // Experiment builds (-DASTC_TUNING_HOOKS) let ASTC_B200_HOST_BAND_MIB override it (tools/e2e_sweep.py).
-    const double src_bytes = double(d_pitch) * double(height);
-    int64_t want_bands = std::max<int64_t>(1, int64_t(std::sqrt(6.7e-7 * src_bytes) + 0.5));
-#ifdef ASTC_TUNING_HOOKS
-    if (const char *env = getenv("ASTC_B200_HOST_BAND_MIB")) {
-        const long v = atol(env);
-        if (v >= 1 && v <= 1024) want_bands = std::max<int64_t>(1, int64_t(src_bytes / (double(v) * 1048576.0) + 0.5));
-    }
-#endif
-    const int64_t rows_per_band = std::max<int64_t>(1, (by + want_bands - 1) / want_bands);
-    const int nbands = int((by + rows_per_band - 1) / rows_per_band);
-    constexpr int kStreams = 3;
-    cudaStream_t streams[kStreams] = {};
-    cudaEvent_t ready = nullptr;
-    uint8_t *d_in = nullptr, *d_out = nullptr;
-    cudaError_t err = cudaSuccess;
-    int created = 0;
-
-    for (; created < kStreams; ++created)
-        if ((err = cudaStreamCreateWithFlags(&streams[created], cudaStreamNonBlocking)) != cudaSuccess) break;
-    if (err == cudaSuccess) err = cudaEventCreateWithFlags(&ready, cudaEventDisableTiming);
-    if (err == cudaSuccess) err = cudaMallocAsync((void **)&d_in, d_pitch * size_t(height), streams[0]);
-    if (err == cudaSuccess) err = cudaMallocAsync((void **)&d_out, size_t(bx * by) * 16u, streams[0]);
-    if (err == cudaSuccess) err = cudaEventRecord(ready, streams[0]);
-    for (int s = 1; s < kStreams && err == cudaSuccess; ++s) err = cudaStreamWaitEvent(streams[s], ready, 0);
-
-    for (int b = 0; b < nbands && err == cudaSuccess; ++b) {
-        cudaStream_t st = streams[b % kStreams];
-        const int64_t r0 = int64_t(b) * rows_per_band, r1 = std::min<int64_t>(by, r0 + rows_per_band);
-        const int64_t y0 = r0 * d, y1 = std::min<int64_t>(int64_t(height), r1 * d);
-        const size_t out_off = size_t(r0 * bx) * 16u, out_bytes = size_t((r1 - r0) * bx) * 16u;
-        err = cudaMemcpy2DAsync(d_in + size_t(y0) * d_pitch, d_pitch, h_rgba + size_t(y0) * pitch_bytes, pitch_bytes,
-                                size_t(width) * 4u, size_t(y1 - y0), cudaMemcpyHostToDevice, st);
-        if (err != cudaSuccess) break;
-        astc::EncodeParams p{};
-        p.single = make_desc(d_in + size_t(y0) * d_pitch, d_out + out_off, d_pitch, width, int(y1 - y0), d, 0);
-        p.count = 1;
-        p.total_blocks = uint64_t(bx) * uint64_t(r1 - r0);
-        err = astc::launch_encode(d, opt->has_alpha != 0, opt->is_normal_map != 0, opt->srgb != 0, opt->axis_method, p, st);
-        if (err != cudaSuccess) break;
-        g_launches.fetch_add(1, std::memory_order_relaxed);
-        err = cudaMemcpyAsync(h_blocks + out_off, d_out + out_off, out_bytes, cudaMemcpyDeviceToHost, st);
-    }
-    for (int s = 0; s < created; ++s) {
-        cudaError_t e2 = cudaStreamSynchronize(streams[s]);
-        if (err == cudaSuccess) err = e2;
-    }
-    if (d_in) cudaFreeAsync(d_in, streams[0]);
-    if (d_out) cudaFreeAsync(d_out, streams[0]);
-    if (created > 0) cudaStreamSynchronize(streams[0]);
-    if (ready) cudaEventDestroy(ready);
-    for (int s = 0; s < created; ++s) cudaStreamDestroy(streams[s]);
-    if (err != cudaSuccess) return cuda_fail(err, "astc_b200_encode_host");
-    return ASTC_B200_OK;
-}
-
 int astc_b200_batch_create(const astc_b200_image *images, int count, const astc_b200_option *opt, astc_b200_batch **out)
 {
     if (!out) return ASTC_B200_ERR_INVALID_ARGUMENT;
@@ -321,6 +216,9 @@ int astc_b200_batch_encode(astc_b200_batch *batch, void *cuda_stream)
 {
     if (!batch) return ASTC_B200_ERR_INVALID_ARGUMENT;
     if (batch->host.empty()) return ASTC_B200_OK;
+    int current = -1;
+    CUDA_TRY(cudaGetDevice(&current));
+    if (current != batch->device_ordinal) return ASTC_B200_ERR_INVALID_ARGUMENT;   // the table and the textures live on the device it was created on
     astc::EncodeParams p{};
     p.single = batch->host[0];
     p.table = batch->device;

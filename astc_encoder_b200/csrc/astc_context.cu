@@ -1,0 +1,406 @@
+// astc_context.cu -- the host-buffer entry points of the C ABI: a persistent per-device context
+// (streams, event, grow-only device workspace, pinned staging) and the two calls built on it,
+//
+//   astc_b200_context_encode_host        load_tex's upload + encode_astc + read_gpu (main.cpp:46-52,
+//                                        astc_encode.h:87-194, astc_save.h:34-50) for ONE texture
+//   astc_b200_context_batch_encode_host  the same for MANY textures (mip chains): pinned staging for the
+//                                        small levels, banded uploads for the large ones, one kernel
+//                                        launch per group of ~64 MiB over a prefix-summed block table
+//
+// The reference creates its device objects once per process (main.cpp:199-209) and its texture / UAV
+// per encode; here the per-call objects are gone too: nothing is created or destroyed on the hot path
+// once the workspace has grown to the largest job seen.  astc_b200_encode_host() (no context argument)
+// runs on a lazily created thread-local context per device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <new>
+#include <vector>
+
+#include "astc_capi_internal.h"
+
+using astc_capi::cuda_fail;
+using astc_capi::dim_of;
+using astc_capi::make_desc;
+
+namespace {
+
+constexpr int kStreams = 3;
+constexpr size_t kSmallImage = 256u << 10;        // sources below this travel through pinned staging (one memcpy beats one cudaMemcpyAsync call)
+constexpr size_t kGroupBytes = 64u << 20;         // source bytes per upload / launch / download group of a batch
+
+template <typename T>
+struct Grow {                                      // grow-only buffer: reallocated only when a job is larger than any before
+    T *ptr = nullptr;
+    size_t cap = 0;
+};
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Host -> device copy of `rows` rows.  A 2-D copy moves row by row -- measured on B200 / PCIe Gen5: 13 GB/s for
+// 4 KB rows against 55 GB/s for one flat copy -- so rows that are contiguous on both sides go as ONE 1-D copy.
+cudaError_t upload_rows(uint8_t *dst, size_t dst_pitch, const uint8_t *src, size_t src_pitch, size_t row_bytes, size_t rows,
+                        cudaStream_t st)
+{
+    if (rows == 0 || row_bytes == 0) return cudaSuccess;
+    if (rows == 1 || (dst_pitch == row_bytes && src_pitch == row_bytes))
+        return cudaMemcpyAsync(dst, src, row_bytes * rows, cudaMemcpyHostToDevice, st);
+    return cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, row_bytes, rows, cudaMemcpyHostToDevice, st);
+}
+
+}  // namespace
+
+struct astc_b200_context {
+    int device = 0;
+    cudaStream_t streams[kStreams] = {};
+    cudaEvent_t ready = nullptr;
+    Grow<uint8_t> d_in, d_out, h_stage_in, h_stage_out;     // device workspace, pinned staging
+    Grow<astc::ImageDesc> d_table;
+
+    ~astc_b200_context()
+    {
+        for (auto &s : streams) if (s) cudaStreamDestroy(s);
+        if (ready) cudaEventDestroy(ready);
+        if (d_in.ptr) cudaFree(d_in.ptr);
+        if (d_out.ptr) cudaFree(d_out.ptr);
+        if (d_table.ptr) cudaFree(d_table.ptr);
+        if (h_stage_in.ptr) cudaFreeHost(h_stage_in.ptr);
+        if (h_stage_out.ptr) cudaFreeHost(h_stage_out.ptr);
+    }
+};
+
+namespace {
+
+template <typename T>
+cudaError_t reserve_device(Grow<T> &g, size_t count)
+{
+    if (count <= g.cap) return cudaSuccess;
+    if (g.ptr) { cudaFree(g.ptr); g.ptr = nullptr; g.cap = 0; }
+    const size_t want = count + count / 8;                     // a little head room: a slightly larger next job does not reallocate
+    cudaError_t e = cudaMalloc((void **)&g.ptr, want * sizeof(T));
+    if (e != cudaSuccess) { cudaGetLastError(); e = cudaMalloc((void **)&g.ptr, count * sizeof(T)); if (e == cudaSuccess) g.cap = count; return e; }
+    g.cap = want;
+    return cudaSuccess;
+}
+
+cudaError_t reserve_pinned(Grow<uint8_t> &g, size_t bytes)
+{
+    if (bytes <= g.cap) return cudaSuccess;
+    if (g.ptr) { cudaFreeHost(g.ptr); g.ptr = nullptr; g.cap = 0; }
+    const cudaError_t e = cudaHostAlloc((void **)&g.ptr, bytes, cudaHostAllocDefault);
+    if (e == cudaSuccess) g.cap = bytes;
+    return e;
+}
+
+int create_context(astc_b200_context **out)
+{
+    *out = nullptr;
+    std::unique_ptr<astc_b200_context> c(new (std::nothrow) astc_b200_context());
+    if (!c) return ASTC_B200_ERR_OUT_OF_MEMORY;
+    CUDA_TRY(cudaGetDevice(&c->device));
+    for (auto &s : c->streams) CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ready, cudaEventDisableTiming));
+    *out = c.release();
+    return ASTC_B200_OK;
+}
+
+// One lazily created context per (host thread, device) behind astc_b200_encode_host().
+astc_b200_context *default_context(int *status)
+{
+    struct Holder {
+        std::vector<astc_b200_context *> per_device;
+        ~Holder() { for (auto *c : per_device) delete c; }
+    };
+    static thread_local Holder holder;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) { *status = cuda_fail(e, "cudaGetDevice"); return nullptr; }
+    if (size_t(dev) >= holder.per_device.size()) holder.per_device.resize(size_t(dev) + 1, nullptr);
+    if (!holder.per_device[dev]) {
+        *status = create_context(&holder.per_device[dev]);
+        if (*status != ASTC_B200_OK) return nullptr;
+    }
+    *status = ASTC_B200_OK;
+    return holder.per_device[dev];
+}
+
+int check_context(const astc_b200_context *ctx)
+{
+    if (!ctx) return ASTC_B200_ERR_INVALID_ARGUMENT;
+    int dev = -1;
+    CUDA_TRY(cudaGetDevice(&dev));
+    return dev == ctx->device ? ASTC_B200_OK : ASTC_B200_ERR_INVALID_ARGUMENT;     // a context belongs to the device it was created on
+}
+
+bool too_many_blocks(int w, int h, int dim)
+{
+    return uint64_t((w + dim - 1) / dim) * uint64_t((h + dim - 1) / dim) > 0x7FFFFFFFull;
+}
+
+cudaError_t sync_all(astc_b200_context *ctx, cudaError_t err)
+{
+    for (auto &s : ctx->streams) {
+        const cudaError_t e2 = cudaStreamSynchronize(s);
+        if (err == cudaSuccess) err = e2;
+    }
+    return err;
+}
+
+}  // namespace
+
+extern "C" {
+
+int astc_b200_context_create(astc_b200_context **ctx)
+{
+    if (!ctx) return ASTC_B200_ERR_INVALID_ARGUMENT;
+    return create_context(ctx);
+}
+
+void astc_b200_context_destroy(astc_b200_context *ctx) { delete ctx; }
+
+int astc_b200_context_trim(astc_b200_context *ctx)
+{
+    const int rc = check_context(ctx);
+    if (rc != ASTC_B200_OK) return rc;
+    CUDA_TRY(sync_all(ctx, cudaSuccess));
+    auto drop = [](auto &g) { if (g.ptr) cudaFree(g.ptr); g.ptr = nullptr; g.cap = 0; };
+    drop(ctx->d_in); drop(ctx->d_out); drop(ctx->d_table);
+    auto droph = [](Grow<uint8_t> &g) { if (g.ptr) cudaFreeHost(g.ptr); g.ptr = nullptr; g.cap = 0; };
+    droph(ctx->h_stage_in); droph(ctx->h_stage_out);
+    return ASTC_B200_OK;
+}
+
+int astc_b200_context_encode_host(astc_b200_context *ctx, const uint8_t *h_rgba, int width, int height, size_t pitch_bytes,
+                                  const astc_b200_option *opt, uint8_t *h_blocks)
+{
+    if (!opt || width < 0 || height < 0 || opt->axis_method > 1) return ASTC_B200_ERR_INVALID_ARGUMENT;
+    if (width == 0 || height == 0) return ASTC_B200_OK;
+    if (!h_rgba || !h_blocks || pitch_bytes < size_t(width) * 4u) return ASTC_B200_ERR_INVALID_ARGUMENT;
+    int rc = check_context(ctx);
+    if (rc != ASTC_B200_OK) return rc;
+    const int d = dim_of(opt);
+    if (too_many_blocks(width, height, d)) return ASTC_B200_ERR_UNSUPPORTED;
+
+    const int64_t bx = (width + d - 1) / d, by = (height + d - 1) / d;
+    // device pitch = the row itself when that keeps rows 16-byte aligned (the kernels' vector path), so a contiguous
+    // host image uploads as flat 1-D copies; padded to 128 B otherwise
+    const size_t row_bytes = size_t(width) * 4u;
+    const size_t d_pitch = row_bytes % 16u == 0 ? row_bytes : align_up(row_bytes, 128);
+    CUDA_TRY(reserve_device(ctx->d_in, d_pitch * size_t(height)));
+    CUDA_TRY(reserve_device(ctx->d_out, size_t(bx * by) * 16u));
+    uint8_t *d_in = ctx->d_in.ptr, *d_out = ctx->d_out.ptr;
+
+    // Bands keep the three engines (H2D, SM, D2H) busy at once.  The H2D copies are the bottleneck and
+    // run back to back; what the banding costs on top is the drain after the last copy (that band's
+    // kernel and its D2H: ~5.2 ps per byte of band) plus ~7.8 us of launch / copy overhead per band
+    // (both measured on B200 / PCIe Gen5: 1 GiB in 1 / 8 / 32 / 128 MiB bands = 28.4 / 20.8 / 20.45 /
+    // 20.9 ms).  The sum is smallest at sqrt(5.2e-12 / 7.8e-6 * bytes) bands: 27 for 1 GiB, 7 for 64 MiB,
+    // one below 1.5 MiB.  Experiment builds (-DASTC_TUNING_HOOKS) let ASTC_B200_HOST_BAND_MIB override it.
+    const double src_bytes = double(d_pitch) * double(height);
+    int64_t want_bands = std::max<int64_t>(1, int64_t(std::sqrt(6.7e-7 * src_bytes) + 0.5));
+#ifdef ASTC_TUNING_HOOKS
+    if (const char *env = getenv("ASTC_B200_HOST_BAND_MIB")) {
+        const long v = atol(env);
+        if (v >= 1 && v <= 1024) want_bands = std::max<int64_t>(1, int64_t(src_bytes / (double(v) * 1048576.0) + 0.5));
+    }
+#endif
+    const int64_t rows_per_band = std::max<int64_t>(1, (by + want_bands - 1) / want_bands);
+    const int nbands = int((by + rows_per_band - 1) / rows_per_band);
+    cudaError_t err = cudaSuccess;
+    for (int b = 0; b < nbands && err == cudaSuccess; ++b) {
+        cudaStream_t st = ctx->streams[b % kStreams];
+        const int64_t r0 = int64_t(b) * rows_per_band, r1 = std::min<int64_t>(by, r0 + rows_per_band);
+        const int64_t y0 = r0 * d, y1 = std::min<int64_t>(int64_t(height), r1 * d);
+        const size_t out_off = size_t(r0 * bx) * 16u, out_bytes = size_t((r1 - r0) * bx) * 16u;
+        err = upload_rows(d_in + size_t(y0) * d_pitch, d_pitch, h_rgba + size_t(y0) * pitch_bytes, pitch_bytes, row_bytes,
+                          size_t(y1 - y0), st);
+        if (err != cudaSuccess) break;
+        astc::EncodeParams p{};
+        p.single = make_desc(d_in + size_t(y0) * d_pitch, d_out + out_off, d_pitch, width, int(y1 - y0), d, 0);
+        p.count = 1;
+        p.total_blocks = uint64_t(bx) * uint64_t(r1 - r0);
+        err = astc::launch_encode(d, opt->has_alpha != 0, opt->is_normal_map != 0, opt->srgb != 0, opt->axis_method, p, st);
+        if (err != cudaSuccess) break;
+        astc_capi::count_launch();
+        err = cudaMemcpyAsync(h_blocks + out_off, d_out + out_off, out_bytes, cudaMemcpyDeviceToHost, st);
+    }
+    // only the streams that were used need to drain
+    for (int s = 0; s < std::min(nbands, kStreams); ++s) {
+        const cudaError_t e2 = cudaStreamSynchronize(ctx->streams[s]);
+        if (err == cudaSuccess) err = e2;
+    }
+    if (err != cudaSuccess) return cuda_fail(err, "astc_b200_context_encode_host");
+    return ASTC_B200_OK;
+}
+
+int astc_b200_encode_host(const uint8_t *h_rgba, int width, int height, size_t pitch_bytes, const astc_b200_option *opt,
+                          uint8_t *h_blocks)
+{
+    if (!opt || width < 0 || height < 0 || opt->axis_method > 1) return ASTC_B200_ERR_INVALID_ARGUMENT;
+    if (width == 0 || height == 0) return ASTC_B200_OK;
+    if (!h_rgba || !h_blocks || pitch_bytes < size_t(width) * 4u) return ASTC_B200_ERR_INVALID_ARGUMENT;
+    int rc = ASTC_B200_OK;
+    astc_b200_context *ctx = default_context(&rc);
+    if (!ctx) return rc;
+    return astc_b200_context_encode_host(ctx, h_rgba, width, height, pitch_bytes, opt, h_blocks);
+}
+
+int astc_b200_context_batch_encode_host(astc_b200_context *ctx, const astc_b200_host_image *images, int count,
+                                        const astc_b200_option *opt)
+{
+    if (!opt || count < 0 || (count > 0 && !images) || opt->axis_method > 1) return ASTC_B200_ERR_INVALID_ARGUMENT;
+    int rc = check_context(ctx);
+    if (rc != ASTC_B200_OK) return rc;
+    const int d = dim_of(opt);
+
+    // ---- plan: arena offsets, block prefix sums per GROUP, which images go through staging ----
+    struct Item {
+        const astc_b200_host_image *im;
+        size_t in_off, in_pitch, in_bytes, out_off, out_bytes, stage_in, stage_out;
+        bool small_in, small_out;
+        uint64_t blocks;
+    };
+    struct Group {
+        size_t first, count;             // items
+        size_t table_first;              // index of its first descriptor
+        uint64_t blocks;
+        size_t out_off, out_bytes;
+    };
+    std::vector<Item> items;
+    std::vector<Group> groups;
+    std::vector<astc::ImageDesc> table;
+    size_t in_total = 0, out_total = 0, stage_in_total = 0, stage_out_total = 0;
+    try {
+        items.reserve(size_t(count));
+        for (int i = 0; i < count; ++i) {
+            const astc_b200_host_image &im = images[i];
+            if (im.width < 0 || im.height < 0) return ASTC_B200_ERR_INVALID_ARGUMENT;
+            if (im.width == 0 || im.height == 0) continue;
+            if (!im.h_rgba || !im.h_blocks || im.pitch_bytes < size_t(im.width) * 4u) return ASTC_B200_ERR_INVALID_ARGUMENT;
+            if (too_many_blocks(im.width, im.height, d)) return ASTC_B200_ERR_UNSUPPORTED;
+            Item it{};
+            it.im = &im;
+            it.in_pitch = align_up(size_t(im.width) * 4u, 16);
+            it.in_bytes = it.in_pitch * size_t(im.height);
+            it.in_off = in_total;
+            in_total += align_up(it.in_bytes, 256);
+            it.blocks = uint64_t((im.width + d - 1) / d) * uint64_t((im.height + d - 1) / d);
+            it.out_bytes = size_t(it.blocks) * 16u;
+            it.out_off = out_total;
+            out_total += it.out_bytes;
+            it.small_in = it.in_bytes < kSmallImage;
+            it.small_out = it.out_bytes < kSmallImage / 4;
+            if (it.small_in) { it.stage_in = stage_in_total; stage_in_total += align_up(it.in_bytes, 256); }   // the arena's padding: runs stay contiguous
+            if (it.small_out) { it.stage_out = stage_out_total; stage_out_total += it.out_bytes; }
+            items.push_back(it);
+        }
+        if (items.empty()) return ASTC_B200_OK;
+        // groups of consecutive images, ~kGroupBytes of source each; block ids restart at 0 in every group
+        table.resize(items.size());
+        for (size_t i = 0; i < items.size();) {
+            Group g{};
+            g.first = i;
+            g.table_first = i;
+            g.out_off = items[i].out_off;
+            size_t bytes = 0;
+            while (i < items.size() && (bytes == 0 || bytes + items[i].in_bytes <= kGroupBytes)) {
+                bytes += items[i].in_bytes;
+                ++i;
+            }
+            g.count = i - g.first;
+            for (size_t k = g.first; k < i; ++k) {
+                const Item &it = items[k];
+                table[k] = make_desc(nullptr, nullptr, it.in_pitch, it.im->width, it.im->height, d, g.blocks);   // pointers filled in below
+                g.blocks += it.blocks;
+                g.out_bytes += it.out_bytes;
+            }
+            groups.push_back(g);
+        }
+    } catch (const std::bad_alloc &) {
+        return ASTC_B200_ERR_OUT_OF_MEMORY;
+    }
+
+    CUDA_TRY(reserve_device(ctx->d_in, in_total));
+    CUDA_TRY(reserve_device(ctx->d_out, out_total));
+    CUDA_TRY(reserve_device(ctx->d_table, table.size()));
+    CUDA_TRY(reserve_pinned(ctx->h_stage_in, stage_in_total));
+    CUDA_TRY(reserve_pinned(ctx->h_stage_out, stage_out_total));
+    for (size_t k = 0; k < items.size(); ++k) {
+        table[k].rgba = ctx->d_in.ptr + items[k].in_off;
+        table[k].blocks = ctx->d_out.ptr + items[k].out_off;
+        table[k].flags = astc_capi::align_flags(table[k].rgba, table[k].pitch);
+    }
+    cudaError_t err = cudaMemcpyAsync(ctx->d_table.ptr, table.data(), table.size() * sizeof(astc::ImageDesc), cudaMemcpyHostToDevice,
+                                      ctx->streams[0]);
+    if (err == cudaSuccess) err = cudaEventRecord(ctx->ready, ctx->streams[0]);
+    for (int s = 1; s < kStreams && err == cudaSuccess; ++s) err = cudaStreamWaitEvent(ctx->streams[s], ctx->ready, 0);
+
+    // ---- per group: uploads, one launch, downloads; groups rotate over the streams ----
+    for (size_t gi = 0; gi < groups.size() && err == cudaSuccess; ++gi) {
+        const Group &g = groups[gi];
+        cudaStream_t st = ctx->streams[gi % kStreams];
+        // small sources: gathered on the host into pinned staging (densely, at the image's device pitch), runs of
+        // consecutive small images uploaded with ONE copy each
+        size_t k = g.first;
+        const size_t end = g.first + g.count;
+        while (k < end && err == cudaSuccess) {
+            const Item &it = items[k];
+            if (!it.small_in) {
+                err = upload_rows(ctx->d_in.ptr + it.in_off, it.in_pitch, it.im->h_rgba, it.im->pitch_bytes,
+                                  size_t(it.im->width) * 4u, size_t(it.im->height), st);
+                ++k;
+                continue;
+            }
+            // a run of small images: consecutive in the batch, hence consecutive -- with the same 256-byte padding --
+            // in the arena and in the staging buffer: gathered by the host, uploaded with one copy
+            size_t run_end = k;
+            while (run_end < end && items[run_end].small_in) ++run_end;
+            for (size_t j = k; j < run_end; ++j) {
+                const Item &sj = items[j];
+                uint8_t *dst = ctx->h_stage_in.ptr + sj.stage_in;
+                const size_t row = size_t(sj.im->width) * 4u;
+                for (int y = 0; y < sj.im->height; ++y)
+                    std::memcpy(dst + size_t(y) * sj.in_pitch, sj.im->h_rgba + size_t(y) * sj.im->pitch_bytes, row);
+            }
+            const Item &last = items[run_end - 1];
+            err = cudaMemcpyAsync(ctx->d_in.ptr + it.in_off, ctx->h_stage_in.ptr + it.stage_in, last.in_off + last.in_bytes - it.in_off,
+                                  cudaMemcpyHostToDevice, st);
+            k = run_end;
+        }
+        if (err != cudaSuccess) break;
+        astc::EncodeParams p{};
+        p.single = table[g.table_first];
+        p.table = g.count > 1 ? ctx->d_table.ptr + g.table_first : nullptr;
+        p.count = int(g.count);
+        p.total_blocks = g.blocks;
+        err = astc::launch_encode(d, opt->has_alpha != 0, opt->is_normal_map != 0, opt->srgb != 0, opt->axis_method, p, st);
+        if (err != cudaSuccess) break;
+        astc_capi::count_launch();
+        // outputs: large ones straight to the caller's buffer; the small ones of the group lie contiguously in the
+        // arena between them, so each run of small outputs is ONE copy into pinned staging, scattered after the sync
+        k = g.first;
+        while (k < end && err == cudaSuccess) {
+            const Item &it = items[k];
+            if (!it.small_out) {
+                err = cudaMemcpyAsync(it.im->h_blocks, ctx->d_out.ptr + it.out_off, it.out_bytes, cudaMemcpyDeviceToHost, st);
+                ++k;
+                continue;
+            }
+            size_t run_end = k, bytes = 0;
+            while (run_end < end && items[run_end].small_out) { bytes += items[run_end].out_bytes; ++run_end; }
+            err = cudaMemcpyAsync(ctx->h_stage_out.ptr + it.stage_out, ctx->d_out.ptr + it.out_off, bytes, cudaMemcpyDeviceToHost, st);
+            k = run_end;
+        }
+    }
+    err = sync_all(ctx, err);
+    if (err != cudaSuccess) return cuda_fail(err, "astc_b200_context_batch_encode_host");
+    for (const Item &it : items)
+        if (it.small_out) std::memcpy(it.im->h_blocks, ctx->h_stage_out.ptr + it.stage_out, it.out_bytes);
+    return ASTC_B200_OK;
+}
+
+}  // extern "C"

@@ -415,6 +415,7 @@ def run_b200(args) -> int:
     # ---- the other BASELINE.json configs, kernel-only, L2 flushed between launches ----
     if world == 1 and not args.no_others:
         line["others"] = other_configs(torch, A, synth, dev, peak)
+        line["e2e_small"] = host_small_textures(torch, A, synth)
     if cfg5 is not None:
         line["config5"] = cfg5
 
@@ -518,6 +519,9 @@ def config5(torch, dist, A, synth, dev, rank, world, barrier, max_over_ranks, fu
 
     both_ms = timed(both)
     launches_per_step = 2
+    host_batch = None
+    if world == 1 and not args.no_host_batch:
+        host_batch = host_batch_e2e(torch, A, srcs, outs, opt, chains, chain_texels)
     total_blocks = int(batch.total_blocks)
     batch.close()
     del srcs, outs, slab2
@@ -534,9 +538,93 @@ def config5(torch, dist, A, synth, dev, rank, world, barrier, max_over_ranks, fu
         "both": {"what": "band launch + batch launch per step (the whole of configs[4])", "ms": round(both_ms, 4),
                  "value": round((texels_a + texels_b) / both_ms / 1e3, 1), "launches_per_step_per_rank": launches_per_step},
     }
+    if host_batch is not None:
+        res["batch"]["e2e_host"] = host_batch
     if single_ms is not None:
         res["band"]["single_gpu_ms_same_run"] = round(single_ms, 4)
         res["band"]["strong_scaling_efficiency"] = round(single_ms / (world * band_ms), 4)
+    return res
+
+
+def _mem_available_gib() -> float:
+    try:
+        for ln in open("/proc/meminfo"):
+            if ln.startswith("MemAvailable:"):
+                return int(ln.split()[1]) / (1 << 20)
+    except OSError:
+        pass
+    return 0.0
+
+
+def host_batch_e2e(torch, A, srcs, outs, opt, chains, chain_texels):
+    """The 512-chain batch END TO END from host memory: astc_b200_context_batch_encode_host with every level in
+    one pinned host buffer (H2D of all levels + kernels + D2H of all blocks inside the timed region), checked
+    against the device-resident batch output."""
+    import numpy as np
+    levels = len(srcs) // chains
+    # pinned memory needed: all sources + all outputs; use fewer chains if the host is short of memory
+    per_chain_in = sum(int(t.numel()) for t in srcs[:levels])
+    per_chain_out = sum(int(t.numel()) for t in outs[:levels])
+    avail = _mem_available_gib() * (1 << 30)
+    use = chains
+    while use > 8 and use * (per_chain_in + per_chain_out) > 0.4 * avail:
+        use //= 2
+    n = use * levels
+    h_in = torch.empty(use * per_chain_in, dtype=torch.uint8, pin_memory=True)
+    h_out = torch.empty(use * per_chain_out, dtype=torch.uint8, pin_memory=True)
+    imgs, dsts, oi, oo = [], [], 0, 0
+    for t, o in zip(srcs[:n], outs[:n]):
+        v = h_in[oi:oi + t.numel()].view(t.shape)
+        v.copy_(t)
+        imgs.append(v.numpy())
+        dsts.append(h_out[oo:oo + o.numel()].view(o.shape).numpy())
+        oi += t.numel()
+        oo += o.numel()
+    torch.cuda.synchronize()
+    ctx = A.Context()
+    ctx.batch_encode_host(imgs, opt, outs=dsts)                   # warm-up: workspace + staging grow here
+    l0 = A.launch_count()
+    ts = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        ctx.batch_encode_host(imgs, opt, outs=dsts)
+        ts.append(time.perf_counter() - t0)
+    launches = (A.launch_count() - l0) // 3
+    ts.sort()
+    same = all(bool(np.array_equal(d, o.cpu().numpy())) for d, o in list(zip(dsts, outs[:n]))[:: max(1, n // 200)])
+    ctx.close()
+    del h_in, h_out
+    return {"api": "astc_b200_context_batch_encode_host (C ABI), every level in pinned host memory", "chains": use, "textures": n,
+            "ms": round(ts[1] * 1e3, 2), "value": round(use * chain_texels / ts[1] / 1e6, 1), "unit": UNIT,
+            "h2d_bytes": use * per_chain_in, "d2h_bytes": use * per_chain_out, "launches_per_call": int(launches),
+            "matches_device_batch": same}
+
+
+def host_small_textures(torch, A, synth):
+    """Per-call cost of astc_b200_encode_host (persistent thread-local context) on small textures, pinned and
+    pageable host memory: what one texture costs end to end when the job is too small to hide anything."""
+    import numpy as np
+    res = []
+    opt = A.encode_option()
+    for size in (4, 256, 1024, 4096):
+        src = synth.synth_rgba(size, size, 11)
+        pinned = torch.empty((size, size, 4), dtype=torch.uint8, pin_memory=True)
+        pinned.copy_(src)
+        pout = torch.empty((A.output_size(size, size, opt) // 16, 16), dtype=torch.uint8, pin_memory=True)
+        row = {"workload": f"{size}x{size} RGBA8, 4x4 RGB, one astc_b200_encode_host call"}
+        for kind, arr, out in (("pinned", pinned.numpy(), pout.numpy()), ("pageable", src.numpy().copy(), np.empty(pout.shape, np.uint8))):
+            for _ in range(5):
+                A.encode_astc_host(arr, opt, out=out)
+            iters = 200 if size <= 1024 else 30
+            ts = []
+            for _ in range(iters):
+                t0 = time.perf_counter()
+                A.encode_astc_host(arr, opt, out=out)
+                ts.append(time.perf_counter() - t0)
+            ts.sort()
+            med = ts[len(ts) // 2]
+            row[kind] = {"us_per_call": round(med * 1e6, 1), "value": round(size * size / med / 1e6, 1), "unit": UNIT}
+        res.append(row)
     return res
 
 
@@ -573,6 +661,7 @@ def main() -> int:
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU oracle baseline / parity sample")
     ap.add_argument("--no-others", action="store_true", help="skip the secondary configs (incl. config 5)")
+    ap.add_argument("--no-host-batch", action="store_true", help="skip the end-to-end host batch of config 5")
     ap.add_argument("--chains", type=int, default=512, help="mip chains in the config-5 batch (default: BASELINE's 512)")
     args = ap.parse_args()
     if args.warmup < 3:

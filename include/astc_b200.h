@@ -119,6 +119,34 @@ ASTC_B200_API int astc_b200_encode_host(const uint8_t *h_rgba, int width, int he
                                         size_t pitch_bytes, const astc_b200_option *opt,
                                         uint8_t *h_blocks);
 
+/* ---- persistent host-side context ---------------------------------------------------------------
+ * What main.cpp creates once per process (device, :199-209) plus what it creates per encode (texture,
+ * UAV, staging buffer: main.cpp:46-52, astc_encode.h:137-164, astc_save.h:19-32), kept alive across
+ * calls: three streams, an event, a grow-only device workspace and pinned staging.  A context belongs
+ * to the device that was current when it was created and to one host thread at a time.
+ * astc_b200_encode_host() uses a lazily created thread-local context, so it pays no per-call setup either. */
+typedef struct astc_b200_context astc_b200_context;
+ASTC_B200_API int astc_b200_context_create(astc_b200_context **ctx);
+ASTC_B200_API void astc_b200_context_destroy(astc_b200_context *ctx);
+ASTC_B200_API int astc_b200_context_trim(astc_b200_context *ctx);     /* give the workspace back; it regrows on demand */
+ASTC_B200_API int astc_b200_context_encode_host(astc_b200_context *ctx, const uint8_t *h_rgba, int width,
+                                                int height, size_t pitch_bytes,
+                                                const astc_b200_option *opt, uint8_t *h_blocks);
+
+/* One texture of a host-memory batch: host pointers (pinned gives full PCIe rate, pageable works). */
+typedef struct astc_b200_host_image {
+    const uint8_t *h_rgba;      /* RGBA8, row-major, row 0 first                 */
+    uint8_t *h_blocks;          /* 16 * ceil(w/D) * ceil(h/D) bytes              */
+    size_t pitch_bytes;         /* >= 4*width                                    */
+    int32_t width, height;
+} astc_b200_host_image;
+/* Upload + encode + read back MANY textures (e.g. whole mip chains) in one synchronous call: levels under
+ * 256 KiB are gathered through pinned staging, larger ones copied directly, ~64 MiB of source per
+ * upload / launch / download group, groups pipelined over the context's streams. */
+ASTC_B200_API int astc_b200_context_batch_encode_host(astc_b200_context *ctx,
+                                                      const astc_b200_host_image *images, int count,
+                                                      const astc_b200_option *opt);
+
 /* Many textures (mip chains) in ONE launch over a prefix-summed block table.
  * create() uploads the table; encode() is asynchronous and reusable.       */
 ASTC_B200_API int astc_b200_batch_create(const astc_b200_image *images, int count,

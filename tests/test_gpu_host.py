@@ -1,0 +1,102 @@
+"""Host-buffer entry points (persistent context, single texture and batch), all through the C ABI and all
+compared with the device path / the oracle.  Reference: load_tex upload + encode_astc + read_gpu
+(main.cpp:46-52, astc_encode.h:87-194, astc_save.h:34-50)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _device_encode(native, img, opt):
+    import torch
+    return native.read_gpu(native.encode_astc(torch.from_numpy(np.ascontiguousarray(img)).cuda(), opt))
+
+
+@pytest.mark.parametrize("dim", [4, 6])
+def test_context_encode_host_sizes_grow_and_shrink(native, oracle, dim):
+    """One context, textures of very different sizes one after the other (the workspace only grows), pinned-free
+    (pageable numpy) memory, ragged sizes, strided rows."""
+    from astc_encoder_b200 import synth
+    ctx = native.Context()
+    opt = native.encode_option(is4x4=dim == 4, is6x6=dim == 6, has_alpha=True, srgb=True)
+    for (w, h) in ((64, 64), (1, 1), (2048, 1024), (250, 187), (4096, 2048), (16, 16), (3, 1000)):
+        img = synth.synth_rgba(w, h, 50 + w).numpy()
+        got = ctx.encode_host(img, opt)
+        assert np.array_equal(got, _device_encode(native, img, opt)), (w, h)
+    wide = synth.synth_rgba(300, 64, 9).numpy()
+    view = wide[:, 10:270]                                              # pitch > 4 * width
+    assert np.array_equal(ctx.encode_host(view, opt), oracle.encode_image(np.ascontiguousarray(view), block_dim=dim, has_alpha=True, srgb=True))
+    ctx.trim()                                                          # workspace released, regrows on demand
+    img = synth.synth_rgba(128, 96, 4).numpy()
+    assert np.array_equal(ctx.encode_host(img, opt), oracle.encode_image(img, block_dim=dim, has_alpha=True, srgb=True))
+    ctx.close()
+
+
+def test_default_context_is_reused_by_encode_host(native):
+    """astc_b200_encode_host (no context argument) runs on a persistent thread-local context: repeated calls
+    give identical results and launch exactly one kernel per small texture."""
+    from astc_encoder_b200 import synth
+    opt = native.encode_option()
+    img = synth.synth_rgba(256, 256, 1).numpy()
+    first = native.encode_astc_host(img, opt)
+    before = native.launch_count()
+    for _ in range(20):
+        assert np.array_equal(native.encode_astc_host(img, opt), first)
+    assert native.launch_count() - before == 20
+
+
+@pytest.mark.parametrize("dim,kw", [(4, dict()), (4, dict(has_alpha=True, srgb=True)), (6, dict(has_alpha=True)), (4, dict(is_normal_map=True)),
+                                    (6, dict(axis_method=1))], ids=str)
+def test_batch_encode_host_mip_chains(native, oracle, dim, kw):
+    """Several whole mip chains + odd-sized textures in one astc_b200_context_batch_encode_host call: large levels
+    copied directly, small ones through pinned staging, several upload/launch/download groups."""
+    import torch
+    from astc_encoder_b200 import synth
+    opt = native.encode_option(is4x4=dim == 4, is6x6=dim == 6, **kw)
+    gen = synth.synth_normal if kw.get("is_normal_map") else synth.synth_rgba
+    images = []
+    for i, size in enumerate((2048, 1024, 512)):
+        images.extend(t.cpu().numpy() for t in native.mip_chain(gen(size, size, 70 + i).cuda()))
+    images.append(synth.synth_rgba(250, 187, 5).numpy())
+    images.append(synth.synth_rgba(3000, 2100, 6).numpy())               # a second group
+    images.append(synth.synth_rgba(300, 64, 7).numpy()[:, 10:270])       # strided rows
+    images.append(synth.synth_rgba(5, 3, 8).numpy())
+    ctx = native.Context()
+    outs = ctx.batch_encode_host(images, opt)
+    okw = {k: v for k, v in kw.items()}
+    for im, o in zip(images, outs):
+        h, w = im.shape[:2]
+        if w * h <= 512 * 512:
+            want = oracle.encode_image(np.ascontiguousarray(im), block_dim=dim, **okw)
+        else:
+            want = _device_encode(native, im, opt)
+        assert np.array_equal(o, want), (w, h)
+    # again into caller-provided outputs, same context (staging and workspace reused)
+    outs2 = [np.zeros_like(o) for o in outs]
+    ctx.batch_encode_host(images, opt, outs=outs2)
+    assert all(np.array_equal(a, b) for a, b in zip(outs, outs2))
+    assert ctx.batch_encode_host([], opt) == []
+    ctx.close()
+
+
+def test_batch_encode_host_pinned_and_errors(native):
+    import torch
+    from astc_encoder_b200 import synth
+    opt = native.encode_option(has_alpha=True)
+    src = synth.synth_rgba(1024, 1024, 3)
+    pinned = torch.empty((1024, 1024, 4), dtype=torch.uint8, pin_memory=True)
+    pinned.copy_(src)
+    ctx = native.Context()
+    a = ctx.batch_encode_host([pinned.numpy()], opt)[0]
+    b = ctx.encode_host(src.numpy(), opt)
+    assert np.array_equal(a, b)
+    L = native.lib()
+    o = opt._abi()
+    assert L.astc_b200_context_encode_host(None, src.numpy().ctypes.data, 8, 8, 32, C.byref(o), a.ctypes.data) == -1
+    assert L.astc_b200_context_encode_host(ctx._h, None, 8, 8, 32, C.byref(o), a.ctypes.data) == -1
+    assert L.astc_b200_context_batch_encode_host(ctx._h, None, 3, C.byref(o)) == -1
+    bad = opt._abi(); bad.axis_method = 7
+    assert L.astc_b200_context_encode_host(ctx._h, src.numpy().ctypes.data, 8, 8, 32, C.byref(bad), a.ctypes.data) == -1
+    ctx.close()
