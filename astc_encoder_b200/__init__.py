@@ -464,9 +464,10 @@ def load_astc(astc_path: str) -> tuple[int, int, int, int, np.ndarray]:
     return xd.value, yd.value, xs.value, ys.value, blocks.reshape(-1, 16)
 
 
-def load_image(path: str, flip_vertically: bool = True) -> np.ndarray:
+def load_image(path: str, flip_vertically: bool = True, with_components: bool = False):
     """stbi_load(path, ..., STBI_rgb_alpha) with the reference's vertical flip
-    (main.cpp:24-25).  Returns (H, W, 4) uint8."""
+    (main.cpp:24-25).  Returns (H, W, 4) uint8; with_components=True also returns the channel
+    count the file held (stbi_load's `comp`)."""
     w, h, comp = C.c_int(), C.c_int(), C.c_int()
     p = C.c_void_p()
     rc = lib().astc_b200_load_image(str(path).encode(), int(flip_vertically), C.byref(w), C.byref(h), C.byref(comp),
@@ -477,7 +478,7 @@ def load_image(path: str, flip_vertically: bool = True) -> np.ndarray:
         arr = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(h.value, w.value, 4)).copy()
     finally:
         lib().astc_b200_free_host_buffer(p)
-    return arr
+    return (arr, comp.value) if with_components else arr
 
 
 def load_tex(tex_path: str, device="cuda", flip_vertically: bool = True):

@@ -18,7 +18,7 @@ CSRC = PKG / "csrc"
 INCLUDE = PKG.parent / "include"
 LIB = PKG / "libastc_b200.so"
 CLI = PKG / "bin" / "astc_cs_enc"
-SOURCES = ("astc_kernels.cu", "astc_capi.cu", "astc_context.cu", "image_io.cpp")
+SOURCES = ("astc_kernels.cu", "astc_capi.cu", "astc_context.cu", "image_io.cpp", "jpeg_io.cpp", "image_formats.cpp")
 
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

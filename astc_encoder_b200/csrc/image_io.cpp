@@ -1,30 +1,34 @@
 // image_io.cpp -- host image ingest: the role stb_image plays in the reference
 // (main.cpp:19-30: stbi_set_flip_vertically_on_load(1); stbi_load(..., STBI_rgb_alpha)).
-// Own decoders on top of zlib: PNG (every colour type / bit depth, tRNS, Adam7),
-// BMP (24/32-bit uncompressed), TGA (true-colour / grey, raw or RLE), PNM (P5/P6).
-// Output is always 8-bit RGBA; `components_in_file` reports what the file held,
-// as stbi_load's `comp` does.  JPEG/GIF/PSD/HDR are not handled (out of scope).
+// Own decoders: PNG (every colour type / bit depth, tRNS, Adam7; zlib) and PNM (P5 / P6) here, JPEG in
+// jpeg_io.cpp, GIF / PSD / HDR / PIC / BMP / TGA in image_formats.cpp -- every format the reference's
+// stb_image v2.22 reads, with its results (tests/test_image_formats.py checks against stb itself).
+// Output is always 8-bit RGBA; `components_in_file` reports what the file held, as stbi_load's `comp` does.
 #include <zlib.h>
 
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <new>
 #include <string>
 #include <vector>
 
 #include "astc_b200.h"
+#include "image_formats.h"
+
+namespace {
+thread_local const char *g_reason = "";
+}
+
+namespace astc_image {
+bool fail(const char *why) { g_reason = why; return false; }
+}  // namespace astc_image
 
 namespace {
 
-thread_local const char *g_reason = "";
-
-bool fail(const char *why) { g_reason = why; return false; }
-
-struct Image {
-    int w = 0, h = 0, comp = 0;
-    std::vector<uint8_t> rgba;
-};
+using astc_image::fail;
+using astc_image::Image;
 
 bool read_file(const char *path, std::vector<uint8_t> &out)
 {
@@ -233,82 +237,6 @@ bool decode_png(const std::vector<uint8_t> &file, Image &img)
     return true;
 }
 
-// ---------------------------------------------------------------- BMP -----
-bool decode_bmp(const std::vector<uint8_t> &f, Image &img)
-{
-    if (f.size() < 54 || f[0] != 'B' || f[1] != 'M') return fail("not BMP");
-    const uint32_t off = le32(&f[10]), hdr = le32(&f[14]);
-    if (hdr < 40) return fail("unsupported BMP header");
-    const int w = int(le32(&f[18]));
-    int h = int(le32(&f[22]));
-    const int bpp = int(le16(&f[28]));
-    const uint32_t comp = le32(&f[30]);
-    const bool top_down = h < 0;
-    if (top_down) h = -h;
-    if (w <= 0 || h <= 0 || (bpp != 24 && bpp != 32) || (comp != 0 && comp != 3)) return fail("unsupported BMP format");
-    const size_t stride = (size_t(w) * size_t(bpp / 8) + 3) & ~size_t(3);
-    if (size_t(off) + stride * size_t(h) > f.size()) return fail("truncated BMP");
-    img.w = w; img.h = h; img.comp = bpp / 8;
-    img.rgba.resize(size_t(w) * size_t(h) * 4);
-    for (int y = 0; y < h; ++y) {
-        const uint8_t *row = &f[size_t(off) + stride * size_t(top_down ? y : h - 1 - y)];
-        for (int x = 0; x < w; ++x) {
-            const uint8_t *p = row + size_t(x) * size_t(bpp / 8);
-            uint8_t *o = &img.rgba[(size_t(y) * size_t(w) + size_t(x)) * 4];
-            o[0] = p[2]; o[1] = p[1]; o[2] = p[0]; o[3] = bpp == 32 ? p[3] : 255;
-        }
-    }
-    return true;
-}
-
-// ---------------------------------------------------------------- TGA -----
-bool decode_tga(const std::vector<uint8_t> &f, Image &img)
-{
-    if (f.size() < 18) return fail("not TGA");
-    const int idlen = f[0], cmap = f[1], type = f[2], w = int(le16(&f[12])), h = int(le16(&f[14])), bpp = f[16], desc = f[17];
-    const bool rle = type == 10 || type == 11, grey = type == 3 || type == 11;
-    if (cmap != 0 || !(type == 2 || type == 3 || type == 10 || type == 11)) return fail("unsupported TGA type");
-    if (w <= 0 || h <= 0 || !((grey && bpp == 8) || (!grey && (bpp == 24 || bpp == 32)))) return fail("unsupported TGA depth");
-    const int bytes = bpp / 8;
-    size_t pos = 18 + size_t(idlen);
-    img.w = w; img.h = h; img.comp = grey ? 1 : bytes;
-    img.rgba.resize(size_t(w) * size_t(h) * 4);
-    const size_t n = size_t(w) * size_t(h);
-    size_t i = 0;
-    uint8_t px[4] = {0, 0, 0, 255};
-    auto fetch = [&]() -> bool {
-        if (pos + size_t(bytes) > f.size()) return false;
-        if (grey) { px[0] = px[1] = px[2] = f[pos]; px[3] = 255; }
-        else { px[0] = f[pos + 2]; px[1] = f[pos + 1]; px[2] = f[pos]; px[3] = bytes == 4 ? f[pos + 3] : 255; }
-        pos += size_t(bytes);
-        return true;
-    };
-    auto store = [&](size_t k) {
-        const size_t y = k / size_t(w), x = k % size_t(w);
-        const size_t yy = (desc & 0x20) ? y : size_t(h) - 1 - y;
-        std::memcpy(&img.rgba[(yy * size_t(w) + x) * 4], px, 4);
-    };
-    while (i < n) {
-        if (!rle) {
-            if (!fetch()) return fail("truncated TGA");
-            store(i++);
-        } else {
-            if (pos >= f.size()) return fail("truncated TGA");
-            const int c = f[pos++], run = (c & 127) + 1;
-            if (c & 128) {
-                if (!fetch()) return fail("truncated TGA");
-                for (int r = 0; r < run && i < n; ++r) store(i++);
-            } else {
-                for (int r = 0; r < run && i < n; ++r) {
-                    if (!fetch()) return fail("truncated TGA");
-                    store(i++);
-                }
-            }
-        }
-    }
-    return true;
-}
-
 // ---------------------------------------------------------------- PNM -----
 bool decode_pnm(const std::vector<uint8_t> &f, Image &img)
 {
@@ -363,11 +291,24 @@ int astc_b200_load_image(const char *path, int flip_vertically, int *width, int 
     if (!read_file(path, file)) return ASTC_B200_ERR_IO;
     Image img;
     bool ok;
-    if (file.size() >= 8 && file[0] == 137 && file[1] == 'P') ok = decode_png(file, img);
-    else if (file.size() >= 2 && file[0] == 'B' && file[1] == 'M') ok = decode_bmp(file, img);
-    else if (file.size() >= 2 && file[0] == 'P' && (file[1] == '5' || file[1] == '6')) ok = decode_pnm(file, img);
-    else if (ends_with_ci(path, ".tga")) ok = decode_tga(file, img);
-    else ok = fail("unknown image type");
+    // format sniffing in stb_image's order (stbi__load_main): JPEG, PNG, BMP, GIF, PSD, PIC, PNM, HDR; TGA, which has
+    // no magic number, last
+    auto starts = [&](const char *magic, size_t n, size_t at = 0) { return file.size() >= at + n && std::memcmp(file.data() + at, magic, n) == 0; };
+    try {
+        if (file.size() >= 3 && file[0] == 0xFF && file[1] == 0xD8) ok = astc_image::decode_jpeg(file, img);
+        else if (file.size() >= 8 && file[0] == 137 && file[1] == 'P') ok = decode_png(file, img);
+        else if (starts("BM", 2)) ok = astc_image::decode_bmp(file, img);
+        else if (starts("GIF8", 4)) ok = astc_image::decode_gif(file, img);
+        else if (starts("8BPS", 4)) ok = astc_image::decode_psd(file, img);
+        else if (starts("\x53\x80\xF6\x34", 4) && starts("PICT", 4, 88)) ok = astc_image::decode_pic(file, img);
+        else if (file.size() >= 2 && file[0] == 'P' && (file[1] == '5' || file[1] == '6')) ok = decode_pnm(file, img);
+        else if (starts("#?RADIANCE\n", 11) || starts("#?RGBE\n", 7)) ok = astc_image::decode_hdr(file, img);
+        else if (astc_image::looks_like_tga(file)) ok = astc_image::decode_tga(file, img);
+        else ok = fail("unknown image type");
+    } catch (const std::bad_alloc &) {                       // a crafted header must not throw through the C ABI
+        g_reason = "outofmem";
+        return ASTC_B200_ERR_OUT_OF_MEMORY;
+    }
     if (!ok) return ASTC_B200_ERR_BAD_IMAGE;
 
     const size_t row = size_t(img.w) * 4;

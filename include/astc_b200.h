@@ -229,8 +229,9 @@ ASTC_B200_API int astc_b200_save_astc_slice(const char *path, int xdim, int ydim
  * astc_b200_free_host_buffer. */
 ASTC_B200_API int astc_b200_load_astc(const char *path, int *xdim, int *ydim, int *xsize, int *ysize,
                                       uint8_t **blocks, size_t *bufsz);
-/* stbi_load(..., STBI_rgb_alpha) with optional vertical flip (main.cpp:24-25):
- * PNG (all colour types / depths, interlace), BMP, TGA, PPM/PGM. */
+/* stbi_load(..., STBI_rgb_alpha) with optional vertical flip (main.cpp:24-25), every format the
+ * reference's stb_image v2.22 reads and with its results: JPEG (baseline + progressive), PNG, BMP, GIF
+ * (first frame), PSD, PIC, PPM/PGM, Radiance HDR (tone-mapped like stbi_load), TGA. */
 ASTC_B200_API int astc_b200_load_image(const char *path, int flip_vertically, int *width, int *height,
                                        int *components_in_file, uint8_t **rgba);
 ASTC_B200_API const char *astc_b200_image_failure_reason(void);
