@@ -35,9 +35,12 @@ __global__ void __launch_bounds__(1024) k(float *out, long long *cyc, float seed
             if (MODE == 3) r[i] = __ffma2_rn(x[i], make_float2(s[i], s[i]), r[i]);
             if (MODE == 4) a[i] = __fmaf_rn(x[i].x, y[i].x, a[i]);
             if (MODE == 5) a[i] = __fmaf_rn(x[i].x, m, a[i]);
-            if (MODE == 6) r[i] = __fmul2_rn(x[i], y[(i + it) & (N - 1)]);     // 2 pairs in, fresh out (not a chain)
+            if (MODE == 6) r[i] = __fmul2_rn(r[i], x[i]);                            // 2 pairs, chain through r
             if (MODE == 7) r[i] = __fadd2_rn(r[i], x[i]);
-            if (MODE == 8) r[i] = __ffma2_rn(x[i], make_float2(s[i], s[i]), y[i]);
+            if (MODE == 8) r[i] = __ffma2_rn(x[i], make_float2(r[i].x, r[i].x), y[i]);     // acc-free: 2 pairs + scalar from the chain
+            if (MODE == 9) r[i] = __fmul2_rn(x[i], make_float2(r[i].x, r[i].x));          // FMUL2 pair * scalar
+            if (MODE == 10) r[i] = __ffma2_rn(x[i], make_float2(s[rep], s[rep]), r[i]);     // scalar shared by the 8 consecutive instructions (reuse cache)
+            if (MODE == 11) r[i] = __ffma2_rn(r[i], make_float2(255.0f, 255.0f), y[i]);     // immediate multiplier
         }
     }
     long long t1 = clock64();
@@ -71,10 +74,13 @@ int main()
     run<1>("FFMA2 r = x*m2+r           (2 varying pairs)");
     run<2>("FFMA2 r = x*y+r            (3 varying pairs)");
     run<3>("FFMA2 r = x*bcast(s)+r     (2 pairs + scalar)");
-    run<8>("FFMA2 r = x*bcast(s)+y     (2 pairs + scalar, fresh dst)");
+    run<8>("FFMA2 r = x*bcast(r.x)+y   (2 pairs + scalar)");
     run<4>("FFMA  a = x*y+a            (3 varying regs)");
     run<5>("FFMA  a = x*m+a            (2 varying regs)");
-    run<6>("FMUL2 r = x*y              (2 varying pairs)");
+    run<6>("FMUL2 r = r*x              (2 varying pairs)");
+    run<9>("FMUL2 r = x*bcast(r.x)     (pair + scalar)");
+    run<10>("FFMA2 r = x*bcast(s)+r     (2 pairs + scalar in reuse)");
+    run<11>("FFMA2 r = r*255+y          (2 pairs + immediate)");
     run<7>("FADD2 r = r+x              (2 varying pairs)");
     return 0;
 }
