@@ -377,7 +377,14 @@ struct Texels6x6 {
     {
         if (k >= kPark6x6) reg[k - kPark6x6] = t;
         else if constexpr (NORMAL) col[k * kThreads6x6] = make_float2(t.lo.x, t.lo.y);
-        else col[k * kThreads6x6] = make_float4(t.lo.x, t.lo.y, t.hi.x, t.hi.y);
+        else {
+            // Written as two 8-byte stores on purpose.  ptxas fuses them back into one STS.128, but allocates the two
+            // packed results (64-bit register pairs) side by side; handed a float4 it re-assembled every texel in a
+            // staging quad with four MOVs -- 104 of a block's 2100 instructions (8192^2 RGB 0.178 -> 0.174 ms, round 2h).
+            const uint32_t a = uint32_t(__cvta_generic_to_shared(col + k * kThreads6x6));
+            asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(t.lo.x), "f"(t.lo.y) : "memory");
+            asm volatile("st.shared.v2.f32 [%0+8], {%1, %2};" ::"r"(a), "f"(t.hi.x), "f"(t.hi.y) : "memory");
+        }
     }
     __device__ __forceinline__ Texel raw_dyn(int k) const
     {

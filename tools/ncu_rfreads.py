@@ -15,7 +15,7 @@ ia = hdr.index("Source"); ie = hdr.index("Instructions Executed")
 NO_DEST = ("ST", "STG", "STS", "STL", "RED", "BAR", "BRA", "EXIT", "BSYNC", "BSSY", "NOP", "LDGSTS", "LDGDEPBAR", "DEPBAR", "ATOMS", "WARPSYNC", "CALL", "RET", "MEMBAR", "ERRBAR", "CCTL")
 reg_re = re.compile(r"^[-|~!]*R(\d+)((?:\.[A-Za-z0-9_]+)*)\|?$")
 addr_re = re.compile(r"\[(?:R(\d+)(\.64|\.U32|\.X\d+)*)?([^\]]*)\]")
-tot_reads = 0; tot_inst = 0; byop = collections.Counter(); by_reads = collections.Counter()
+tot_reads = 0; tot_inst = 0; tot_cost = 0.0; byop = collections.Counter(); by_reads = collections.Counter()
 prev_reuse = {}
 for r in rows[1:]:
     if len(r) <= ie: continue
@@ -47,10 +47,13 @@ for r in rows[1:]:
             if ".reuse" in suf: cur_reuse[slot] = reg
         slot += 1
     prev_reuse = cur_reuse
+    pipe = 2.0 if op in ("FFMA2", "FMUL2", "FADD2") else 1.0
+    tot_cost += max(pipe, reads / 2) * n
     tot_reads += reads * n; tot_inst += n
     byop[op] += reads * n; by_reads[reads] += n
 warps = int(sys.argv[2]) if len(sys.argv) > 2 else max(int(r[ie] or 0) for r in rows[1:] if len(r) > ie)
 print(f"warp-instructions per warp {tot_inst / warps:.1f}; RF operand reads per warp {tot_reads / warps:.1f} -> {tot_reads / warps / 2:.1f} cycles at 2 reads/clk")
+print(f"per-instruction model sum of max(issue or pipe cycles, reads / 2): {tot_cost / warps:.1f} cycles per warp (validated per phase in profiles/r2h_phase_model.txt)")
 for op, n in byop.most_common(14):
     print(f"  {op:8s} {n / warps:8.1f} reads")
 print("  reads/instr histogram:", {k: round(v / warps, 1) for k, v in sorted(by_reads.items())})
