@@ -289,18 +289,21 @@ encode4x4_kernel(const EncodeParams p)
     __shared__ dev::SharedTables st;
     __shared__ uint4 s_rows[2][4][kThreads4x4];                 // cp.async landing slots, double-buffered
     __shared__ __align__(16) float s_lut_a[SRGB ? 256 : 4];
-    load_shared_tables<ALPHA, SRGB, true>(st);
-    if (SRGB) load_alpha_lut(s_lut_a);
-    __syncthreads();
-    const uint32_t s_field = smem_addr(st.field), s_trit = smem_addr(st.trit_scattered);
     const uint32_t slot0 = smem_addr(&s_rows[0][0][threadIdx.x]);
     constexpr uint32_t kSlotStride = 4u * kThreads4x4 * 16u;
 
     // CTA b owns ids [b*BPT*T, (b+1)*BPT*T); pass i takes the i-th run of T consecutive ids, so a
     // warp reads 512 contiguous bytes per texel row and stores 512 contiguous bytes.
+    // The first block's rows are requested BEFORE the tables are fetched: the two HBM / L2 round trips of a
+    // CTA's start-up then overlap instead of following each other (the landing slots do not alias the tables).
     Walk<BATCH> wk;
-    if (!wk.start(p, uint64_t(blockIdx.x) * uint32_t(p.passes * kThreads4x4) + threadIdx.x)) return;
-    bool fast = prefetch_rows4x4<BATCH>(p, wk, slot0);
+    const bool any = wk.start(p, uint64_t(blockIdx.x) * uint32_t(p.passes * kThreads4x4) + threadIdx.x);
+    bool fast = any && prefetch_rows4x4<BATCH>(p, wk, slot0);
+    load_shared_tables<ALPHA, SRGB, true>(st);
+    if (SRGB) load_alpha_lut(s_lut_a);
+    __syncthreads();
+    if (!any) return;
+    const uint32_t s_field = smem_addr(st.field), s_trit = smem_addr(st.trit_scattered);
 #pragma unroll 1
     for (int pass = 0;; ++pass) {
         Texels4x4 tx;
@@ -414,14 +417,24 @@ encode6x6_kernel(const EncodeParams p)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typename TX::Slot *s_tex = reinterpret_cast<typename TX::Slot *>(smem_raw);         // [kPark6x6][kThreads6x6]
     dev::SharedTables &st = *reinterpret_cast<dev::SharedTables *>(s_tex + kPark6x6 * kThreads6x6);
-    load_shared_tables<ALPHA, SRGB, false>(st);
-    __syncthreads();
-    const uint32_t s_field = smem_addr(st.field), s_trit = smem_addr(st.trit_scattered);
-
     // CTA b owns ids [b*BPT*T, (b+1)*BPT*T); a thread re-uses its own shared-memory column for
     // each of its blocks (only it reads or writes that column: no barrier between passes).
+    // The first block's rows are pulled towards L2 before the tables are fetched, so that the two round trips of
+    // a CTA's start-up overlap.
     Walk<BATCH> wk;
-    if (!wk.start(p, uint64_t(blockIdx.x) * uint32_t(p.passes * kThreads6x6) + threadIdx.x)) return;
+    const bool any = wk.start(p, uint64_t(blockIdx.x) * uint32_t(p.passes * kThreads6x6) + threadIdx.x);
+    if (any) {
+        const ImageDesc &d0 = wk.desc(p);
+        if (wk.by * 6u + 6u <= uint32_t(d0.height) && wk.bx * 6u + 6u <= uint32_t(d0.width)) {
+            const uint8_t *b0 = d0.rgba + size_t(wk.by * 6u) * d0.pitch + size_t(wk.bx * 6u) * 4u;
+#pragma unroll
+            for (int r = 0; r < 6; ++r) asm volatile("prefetch.global.L2 [%0];" ::"l"(b0 + size_t(r) * d0.pitch));
+        }
+    }
+    load_shared_tables<ALPHA, SRGB, false>(st);
+    __syncthreads();
+    if (!any) return;
+    const uint32_t s_field = smem_addr(st.field), s_trit = smem_addr(st.trit_scattered);
 #pragma unroll 1
     for (int pass = 0;; ++pass) {
         f2 sum_lo = dev::bc(0.f), sum_hi = dev::bc(0.f);
