@@ -231,23 +231,39 @@ def _effective(option: encode_option, srgb_texture: Optional[bool]) -> _Option:
     return o
 
 
+def _check_src(src):
+    """The source-tensor contract of every device entry point: CUDA uint8 (H, W, 4), texels packed,
+    rows may be strided.  Returns (h, w, pitch_bytes)."""
+    import torch
+    if not (isinstance(src, torch.Tensor) and src.is_cuda and src.dtype == torch.uint8 and src.dim() == 3
+            and src.shape[2] == 4 and src.stride(2) == 1 and src.stride(1) == 4):
+        raise ValueError("src must be a CUDA uint8 tensor of shape (H, W, 4) with packed texels")
+    h, w = int(src.shape[0]), int(src.shape[1])
+    return h, w, (int(src.stride(0)) if h > 1 else w * 4)
+
+
+def _check_out(out, nbytes: int, device) -> None:
+    import torch
+    if not (isinstance(out, torch.Tensor) and out.is_cuda and out.dtype == torch.uint8 and out.is_contiguous()
+            and out.numel() >= nbytes):
+        raise ValueError("out must be a contiguous CUDA uint8 tensor of at least output_size bytes")
+    if out.device != device:
+        raise ValueError(f"out is on {out.device}, the source on {device}")
+
+
 def encode_astc(src, option: encode_option, out=None, stream=None, srgb_texture: Optional[bool] = None):
     """encode_astc (astc_encode.h:87): `src` is a CUDA uint8 tensor (H, W, 4), rows may be
     strided; returns a CUDA uint8 tensor (blocks, 16).  Asynchronous on `stream`
     (default: torch's current stream), like the reference's Dispatch.
     `srgb_texture` overrides option.srgb the way the texture format does (main.cpp:214)."""
     import torch
-    if not (isinstance(src, torch.Tensor) and src.is_cuda and src.dtype == torch.uint8 and src.dim() == 3
-            and src.shape[2] == 4 and src.stride(2) == 1 and src.stride(1) == 4):
-        raise ValueError("src must be a CUDA uint8 tensor of shape (H, W, 4) with packed texels")
-    h, w = int(src.shape[0]), int(src.shape[1])
-    pitch = int(src.stride(0)) if h > 1 else w * 4
+    h, w, pitch = _check_src(src)
     o = _effective(option, srgb_texture)
     nbytes = int(lib().astc_b200_output_size(w, h, C.byref(o)))
     if out is None:
         out = torch.empty((nbytes // BLOCK_BYTES, BLOCK_BYTES), dtype=torch.uint8, device=src.device)
-    elif not (out.is_cuda and out.dtype == torch.uint8 and out.is_contiguous() and out.numel() >= nbytes):
-        raise ValueError("out must be a contiguous CUDA uint8 tensor of at least output_size bytes")
+    else:
+        _check_out(out, nbytes, src.device)
     with torch.cuda.device(src.device):
         _check(lib().astc_b200_encode_device(src.data_ptr(), w, h, pitch, C.byref(o), out.data_ptr(),
                                              _stream_ptr(stream)), "encode_astc")
@@ -331,10 +347,13 @@ class Context:
 def read_gpu(buffer, stream=None) -> np.ndarray:
     """read_gpu (astc_save.h:34-50): download the block buffer and synchronise."""
     import torch
+    if not (isinstance(buffer, torch.Tensor) and buffer.is_cuda and buffer.is_contiguous()):
+        raise ValueError("buffer must be a contiguous CUDA tensor")
     host = torch.empty(buffer.shape, dtype=buffer.dtype, pin_memory=True)
-    s = _stream_ptr(stream)
-    _check(lib().astc_b200_memcpy_d2h(host.data_ptr(), buffer.data_ptr(), buffer.numel(), s), "read_gpu")
-    _check(lib().astc_b200_stream_synchronize(s), "read_gpu")
+    with torch.cuda.device(buffer.device):
+        s = _stream_ptr(stream)
+        _check(lib().astc_b200_memcpy_d2h(host.data_ptr(), buffer.data_ptr(), buffer.numel() * buffer.element_size(), s), "read_gpu")
+        _check(lib().astc_b200_stream_synchronize(s), "read_gpu")
     return host.numpy().copy()
 
 
@@ -346,23 +365,38 @@ class Batch:
         import torch
         self.option = option
         self.sources = list(sources)
+        self._handle = None
         o = option._abi()
+        # the same tensor contract as encode_astc for every source and output; one device for the whole batch
+        # (the descriptor table and the launch live on it -- astc_b200_batch_encode checks the ordinal again)
+        geom = [_check_src(s) for s in self.sources]
+        self.device = self.sources[0].device if self.sources else torch.device("cuda", torch.cuda.current_device())
+        for s in self.sources:
+            if s.device != self.device:
+                raise ValueError(f"mixed-device batch: {s.device} and {self.device}")
+        sizes = [output_size(w, h, option) for h, w, _ in geom]
         if outputs is None:
-            outputs = [torch.empty((output_size(int(s.shape[1]), int(s.shape[0]), option) // BLOCK_BYTES, BLOCK_BYTES),
-                                   dtype=torch.uint8, device=s.device) for s in self.sources]
+            outputs = [torch.empty((n // BLOCK_BYTES, BLOCK_BYTES), dtype=torch.uint8, device=self.device) for n in sizes]
         self.outputs = list(outputs)
+        if len(self.outputs) != len(self.sources):
+            raise ValueError("one output per source")
+        for d, n in zip(self.outputs, sizes):
+            _check_out(d, n, self.device)
         imgs = (_Image * max(1, len(self.sources)))()
-        for i, (s, d) in enumerate(zip(self.sources, self.outputs)):
-            h, w = int(s.shape[0]), int(s.shape[1])
-            imgs[i] = _Image(s.data_ptr(), d.data_ptr(), int(s.stride(0)) if h > 1 else w * 4, w, h)
-        self._handle = C.c_void_p()
-        _check(lib().astc_b200_batch_create(imgs, len(self.sources), C.byref(o), C.byref(self._handle)), "Batch")
+        for i, (s, d, (h, w, pitch)) in enumerate(zip(self.sources, self.outputs, geom)):
+            imgs[i] = _Image(s.data_ptr(), d.data_ptr(), pitch, w, h)
+        handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _check(lib().astc_b200_batch_create(imgs, len(self.sources), C.byref(o), C.byref(handle)), "Batch")
+        self._handle = handle
         nb, nt = C.c_uint64(), C.c_uint64()
         lib().astc_b200_batch_total_blocks(self._handle, C.byref(nb), C.byref(nt))
         self.total_blocks, self.total_texels = nb.value, nt.value
 
     def encode(self, stream=None):
-        _check(lib().astc_b200_batch_encode(self._handle, _stream_ptr(stream)), "Batch.encode")
+        import torch
+        with torch.cuda.device(self.device):
+            _check(lib().astc_b200_batch_encode(self._handle, _stream_ptr(stream)), "Batch.encode")
         return self.outputs
 
     def close(self):
@@ -380,9 +414,16 @@ class Batch:
 def decode_astc(blocks, width: int, height: int, dim: int, stream=None):
     """Device decode of the subset this encoder emits -> CUDA uint8 (H, W, 4)."""
     import torch
+    if not (isinstance(blocks, torch.Tensor) and blocks.is_cuda and blocks.dtype == torch.uint8 and blocks.is_contiguous()):
+        raise ValueError("blocks must be a contiguous CUDA uint8 tensor")
+    if dim not in (4, 6):
+        raise ValueError("dim must be 4 or 6")
+    if blocks.numel() < ((width + dim - 1) // dim) * ((height + dim - 1) // dim) * BLOCK_BYTES:
+        raise ValueError("blocks is smaller than the block grid of a width x height texture")
     out = torch.empty((height, width, 4), dtype=torch.uint8, device=blocks.device)
-    _check(lib().astc_b200_decode_device(blocks.data_ptr(), width, height, dim, out.data_ptr(), width * 4,
-                                         _stream_ptr(stream)), "decode_astc")
+    with torch.cuda.device(blocks.device):
+        _check(lib().astc_b200_decode_device(blocks.data_ptr(), width, height, dim, out.data_ptr(), width * 4,
+                                             _stream_ptr(stream)), "decode_astc")
     return out
 
 

@@ -235,3 +235,35 @@ def test_oracle_mufu_emulation_matches_the_device(native, oracle):
     ok = (x > 2.0 ** -125) & (x < 2.0 ** 125)                 # reciprocals that stay normal (ftz beyond)
     got_rcp = native.mufu("rcp", d).cpu().numpy()
     assert np.array_equal(got_rcp.view(np.uint32)[ok], oracle.mufu_rcp(x).view(np.uint32)[ok])
+
+
+def test_batch_and_decode_reject_malformed_tensors(native):
+    """Batch applies encode_astc's tensor contract to every source and output: a permuted or
+    sliced-in-x tensor, a short or non-contiguous output and a wrong dtype are errors, not garbage."""
+    import torch
+    opt = native.encode_option()
+    good = torch.zeros((16, 16, 4), dtype=torch.uint8, device="cuda")
+    with pytest.raises(ValueError):
+        native.Batch([good.permute(1, 0, 2)], opt)                       # texels not packed along x
+    with pytest.raises(ValueError):
+        native.Batch([good[:, ::2]], opt)                                # stride(1) != 4
+    with pytest.raises(ValueError):
+        native.Batch([good.to(torch.int8)], opt)
+    with pytest.raises(ValueError):
+        native.Batch([good.cpu()], opt)
+    with pytest.raises(ValueError):
+        native.Batch([good], opt, outputs=[torch.zeros(15 * 16, dtype=torch.uint8, device="cuda")])      # too small
+    with pytest.raises(ValueError):
+        native.Batch([good], opt, outputs=[torch.zeros((32, 16), dtype=torch.uint8, device="cuda")[::2]])  # not contiguous
+    with pytest.raises(ValueError):
+        native.Batch([good, good], opt, outputs=[torch.zeros((16, 16), dtype=torch.uint8, device="cuda")])
+    rows = good[::2]                                                     # strided ROWS are fine
+    b = native.Batch([rows], opt)
+    b.encode()
+    torch.cuda.synchronize()
+    assert b.outputs[0].shape == (2 * 4, 16)
+    b.close()
+    with pytest.raises(ValueError):
+        native.decode_astc(torch.zeros((3, 16), dtype=torch.uint8, device="cuda"), 16, 16, 4)              # 16 blocks needed
+    with pytest.raises(ValueError):
+        native.decode_astc(torch.zeros((16, 16), dtype=torch.uint8, device="cuda"), 16, 16, 5)
