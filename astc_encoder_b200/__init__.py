@@ -120,6 +120,7 @@ _SIGNATURES = {
     "astc_b200_context_create": (C.c_int, [C.POINTER(C.c_void_p)]),
     "astc_b200_context_destroy": (None, [C.c_void_p]),
     "astc_b200_context_trim": (C.c_int, [C.c_void_p]),
+    "astc_b200_context_set_copy_threads": (C.c_int, [C.c_void_p, C.c_int]),
     "astc_b200_context_encode_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.POINTER(_Option), C.c_void_p]),
     "astc_b200_context_batch_encode_host": (C.c_int, [C.c_void_p, C.POINTER(_HostImage), C.c_int, C.POINTER(_Option)]),
     "astc_b200_batch_create": (C.c_int, [C.POINTER(_Image), C.c_int, C.POINTER(_Option), C.POINTER(C.c_void_p)]),
@@ -331,6 +332,10 @@ class Context:
 
     def trim(self) -> None:
         _check(lib().astc_b200_context_trim(self._h), "Context.trim")
+
+    def set_copy_threads(self, threads: int) -> None:
+        """Worker threads of the staged (pageable-memory) pipeline besides the caller: -1 automatic, 0 none."""
+        _check(lib().astc_b200_context_set_copy_threads(self._h, int(threads)), "Context.set_copy_threads")
 
     def close(self) -> None:
         if getattr(self, "_h", None):

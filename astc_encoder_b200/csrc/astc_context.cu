@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "astc_capi_internal.h"
+#include "host_copy_pool.h"
 
 using astc_capi::cuda_fail;
 using astc_capi::dim_of;
@@ -32,6 +33,8 @@ namespace {
 constexpr int kStreams = 3;
 constexpr size_t kSmallImage = 256u << 10;        // sources below this travel through pinned staging (one memcpy beats one cudaMemcpyAsync call)
 constexpr size_t kGroupBytes = 64u << 20;         // source bytes per upload / launch / download group of a batch
+constexpr size_t kStagedMin = 1u << 20;           // pageable textures from this size on go through the staged pipeline below
+constexpr size_t kStagedBand = 4u << 20;          // source bytes per staged band (one pinned slot per stream)
 
 template <typename T>
 struct Grow {                                      // grow-only buffer: reallocated only when a job is larger than any before
@@ -52,19 +55,37 @@ cudaError_t upload_rows(uint8_t *dst, size_t dst_pitch, const uint8_t *src, size
     return cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, row_bytes, rows, cudaMemcpyHostToDevice, st);
 }
 
+// Pageable host memory (what the reference's caller has: stbi_load's malloc, `new uint8_t[]`, main.cpp:24,224).
+// cudaMemcpyAsync from such a buffer is staged by the driver on the calling thread at ~11 GB/s (measured on the
+// B200 box, against 55 GB/s from pinned memory).  The staged pipeline of astc_b200_context_encode_host does that
+// staging itself, into pinned slots, with a few worker threads: the host memcpy then runs at the rate of several
+// cores and overlaps the DMA and the kernel of the bands before it.
+bool is_pageable(const void *p)
+{
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
 }  // namespace
 
 struct astc_b200_context {
     int device = 0;
     cudaStream_t streams[kStreams] = {};
     cudaEvent_t ready = nullptr;
+    cudaEvent_t slot_done[kStreams] = {};                   // staged pipeline: the band that used slot s has left it
     Grow<uint8_t> d_in, d_out, h_stage_in, h_stage_out;     // device workspace, pinned staging
     Grow<astc::ImageDesc> d_table;
+    astc_host::CopyPool pool;
 
     ~astc_b200_context()
     {
         for (auto &s : streams) if (s) cudaStreamDestroy(s);
         if (ready) cudaEventDestroy(ready);
+        for (auto &e : slot_done) if (e) cudaEventDestroy(e);
         if (d_in.ptr) cudaFree(d_in.ptr);
         if (d_out.ptr) cudaFree(d_out.ptr);
         if (d_table.ptr) cudaFree(d_table.ptr);
@@ -104,6 +125,7 @@ int create_context(astc_b200_context **out)
     CUDA_TRY(cudaGetDevice(&c->device));
     for (auto &s : c->streams) CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&c->ready, cudaEventDisableTiming));
+    for (auto &e : c->slot_done) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     *out = c.release();
     return ASTC_B200_OK;
 }
@@ -162,6 +184,13 @@ int astc_b200_context_create(astc_b200_context **ctx)
 
 void astc_b200_context_destroy(astc_b200_context *ctx) { delete ctx; }
 
+int astc_b200_context_set_copy_threads(astc_b200_context *ctx, int threads)
+{
+    if (!ctx || threads < -1 || threads > 64) return ASTC_B200_ERR_INVALID_ARGUMENT;
+    ctx->pool.set_workers(threads);
+    return ASTC_B200_OK;
+}
+
 int astc_b200_context_trim(astc_b200_context *ctx)
 {
     const int rc = check_context(ctx);
@@ -193,6 +222,74 @@ int astc_b200_context_encode_host(astc_b200_context *ctx, const uint8_t *h_rgba,
     CUDA_TRY(reserve_device(ctx->d_in, d_pitch * size_t(height)));
     CUDA_TRY(reserve_device(ctx->d_out, size_t(bx * by) * 16u));
     uint8_t *d_in = ctx->d_in.ptr, *d_out = ctx->d_out.ptr;
+
+    // Pageable source and / or destination of at least 1 MiB: the staged pipeline.  Band b uses stream and pinned
+    // slot b % 3: [workers copy its rows into the slot] -> flat H2D -> kernel -> D2H [into the slot] -> event;
+    // before slot s is refilled, the band that used it three bands ago is retired (event wait, then its blocks
+    // are copied out to the caller's buffer).  The host copies of band b overlap the DMA and kernels of b-1, b-2.
+    const bool big = d_pitch * size_t(height) >= kStagedMin;            // (the pointer queries cost ~1 us each: not on small textures)
+    const bool stage_in = big && is_pageable(h_rgba), stage_out = big && is_pageable(h_blocks);
+    if (stage_in || stage_out) {
+        // bands of a quarter of the texture, between 512 KiB and 4 MiB: even a 1 MiB texture overlaps its copies
+        const size_t band_bytes = std::min(kStagedBand, std::max<size_t>(512u << 10, d_pitch * size_t(height) / 4u));
+        const int64_t rows_pb = std::max<int64_t>(1, int64_t(band_bytes / (d_pitch * size_t(d))));      // block rows per band
+        const int nb = int((by + rows_pb - 1) / rows_pb);
+        const size_t in_slot = size_t(rows_pb) * size_t(d) * d_pitch, out_slot = size_t(rows_pb * bx) * 16u;
+        if (stage_in) CUDA_TRY(reserve_pinned(ctx->h_stage_in, in_slot * kStreams));
+        if (stage_out) CUDA_TRY(reserve_pinned(ctx->h_stage_out, out_slot * kStreams));
+        auto out_range = [&](int b, size_t &off, size_t &bytes) {
+            const int64_t r0 = int64_t(b) * rows_pb, r1 = std::min<int64_t>(by, r0 + rows_pb);
+            off = size_t(r0 * bx) * 16u;
+            bytes = size_t((r1 - r0) * bx) * 16u;
+        };
+        auto retire = [&](int b) -> cudaError_t {                       // band b is complete: hand its blocks over
+            const int s = b % kStreams;
+            const cudaError_t e = cudaEventSynchronize(ctx->slot_done[s]);
+            if (e != cudaSuccess || !stage_out) return e;
+            size_t off, bytes;
+            out_range(b, off, bytes);
+            ctx->pool.copy_rows(h_blocks + off, bytes, ctx->h_stage_out.ptr + size_t(s) * out_slot, bytes, bytes, 1);
+            return cudaSuccess;
+        };
+        cudaError_t err = cudaSuccess;
+        int retired = 0;
+        for (int b = 0; b < nb && err == cudaSuccess; ++b) {
+            const int s = b % kStreams;
+            cudaStream_t st = ctx->streams[s];
+            if (b >= kStreams) { err = retire(b - kStreams); ++retired; if (err != cudaSuccess) break; }
+            const int64_t r0 = int64_t(b) * rows_pb, r1 = std::min<int64_t>(by, r0 + rows_pb);
+            const int64_t y0 = r0 * d, y1 = std::min<int64_t>(int64_t(height), r1 * d);
+            uint8_t *d_band = d_in + size_t(y0) * d_pitch;
+            if (stage_in) {
+                uint8_t *slot = ctx->h_stage_in.ptr + size_t(s) * in_slot;
+                ctx->pool.copy_rows(slot, d_pitch, h_rgba + size_t(y0) * pitch_bytes, pitch_bytes, row_bytes, size_t(y1 - y0),
+                                    /*streaming=*/true);            // only the DMA engine reads the slot
+                // the padding between row_bytes and d_pitch (rows that are not a multiple of 16 bytes) is never read
+                err = cudaMemcpyAsync(d_band, slot, size_t(y1 - y0 - 1) * d_pitch + row_bytes, cudaMemcpyHostToDevice, st);
+            } else {
+                err = upload_rows(d_band, d_pitch, h_rgba + size_t(y0) * pitch_bytes, pitch_bytes, row_bytes, size_t(y1 - y0), st);
+            }
+            if (err != cudaSuccess) break;
+            size_t out_off, out_bytes;
+            out_range(b, out_off, out_bytes);
+            astc::EncodeParams p{};
+            p.single = make_desc(d_band, d_out + out_off, d_pitch, width, int(y1 - y0), d, 0);
+            p.count = 1;
+            p.total_blocks = uint64_t(bx) * uint64_t(r1 - r0);
+            err = astc::launch_encode(d, opt->has_alpha != 0, opt->is_normal_map != 0, opt->srgb != 0, opt->axis_method, p, st);
+            if (err != cudaSuccess) break;
+            astc_capi::count_launch();
+            err = cudaMemcpyAsync(stage_out ? ctx->h_stage_out.ptr + size_t(s) * out_slot : h_blocks + out_off, d_out + out_off, out_bytes,
+                                  cudaMemcpyDeviceToHost, st);
+            if (err == cudaSuccess) err = cudaEventRecord(ctx->slot_done[s], st);
+        }
+        for (int b = retired; b < nb && err == cudaSuccess; ++b) err = retire(b);
+        if (err != cudaSuccess) {
+            sync_all(ctx, err);
+            return cuda_fail(err, "astc_b200_context_encode_host (staged)");
+        }
+        return ASTC_B200_OK;
+    }
 
     // Bands keep the three engines (H2D, SM, D2H) busy at once.  The H2D copies are the bottleneck and
     // run back to back; what the banding costs on top is the drain after the last copy (that band's
@@ -257,23 +354,26 @@ int astc_b200_context_batch_encode_host(astc_b200_context *ctx, const astc_b200_
     if (rc != ASTC_B200_OK) return rc;
     const int d = dim_of(opt);
 
-    // ---- plan: arena offsets, block prefix sums per GROUP, which images go through staging ----
+    // ---- plan: arena offsets, block prefix sums per GROUP, which images travel through the pinned slots ----
+    // An image goes through a slot when it is small (one host memcpy beats one cudaMemcpyAsync call) or when it lies
+    // in PAGEABLE memory (the copy workers beat the driver's own staging 2-3x); large pinned images are copied
+    // straight from / to the caller's buffer.  A group's slot mirrors the group's stretch of the device arena, so
+    // every run of consecutive slot images is uploaded -- and every run of slot outputs downloaded -- with ONE copy.
     struct Item {
         const astc_b200_host_image *im;
-        size_t in_off, in_pitch, in_bytes, out_off, out_bytes, stage_in, stage_out;
-        bool small_in, small_out;
+        size_t in_off, in_pitch, in_bytes, out_off, out_bytes;
+        bool via_in, via_out;
         uint64_t blocks;
     };
     struct Group {
         size_t first, count;             // items
-        size_t table_first;              // index of its first descriptor
         uint64_t blocks;
-        size_t out_off, out_bytes;
+        size_t in_off, in_span, out_off, out_bytes;
     };
     std::vector<Item> items;
     std::vector<Group> groups;
     std::vector<astc::ImageDesc> table;
-    size_t in_total = 0, out_total = 0, stage_in_total = 0, stage_out_total = 0;
+    size_t in_total = 0, out_total = 0, slot_in = 0, slot_out = 0;
     try {
         items.reserve(size_t(count));
         for (int i = 0; i < count; ++i) {
@@ -292,10 +392,10 @@ int astc_b200_context_batch_encode_host(astc_b200_context *ctx, const astc_b200_
             it.out_bytes = size_t(it.blocks) * 16u;
             it.out_off = out_total;
             out_total += it.out_bytes;
-            it.small_in = it.in_bytes < kSmallImage;
-            it.small_out = it.out_bytes < kSmallImage / 4;
-            if (it.small_in) { it.stage_in = stage_in_total; stage_in_total += align_up(it.in_bytes, 256); }   // the arena's padding: runs stay contiguous
-            if (it.small_out) { it.stage_out = stage_out_total; stage_out_total += it.out_bytes; }
+            // (images above a group's size never go through a slot: the slots stay bounded; the pointer query costs
+            // about a microsecond, so it is skipped for images that take the slot anyway)
+            it.via_in = it.in_bytes < kSmallImage || (it.in_bytes <= kGroupBytes && is_pageable(im.h_rgba));
+            it.via_out = it.out_bytes < kSmallImage / 4 || (it.in_bytes <= kGroupBytes && is_pageable(im.h_blocks));
             items.push_back(it);
         }
         if (items.empty()) return ASTC_B200_OK;
@@ -304,7 +404,7 @@ int astc_b200_context_batch_encode_host(astc_b200_context *ctx, const astc_b200_
         for (size_t i = 0; i < items.size();) {
             Group g{};
             g.first = i;
-            g.table_first = i;
+            g.in_off = items[i].in_off;
             g.out_off = items[i].out_off;
             size_t bytes = 0;
             while (i < items.size() && (bytes == 0 || bytes + items[i].in_bytes <= kGroupBytes)) {
@@ -312,12 +412,18 @@ int astc_b200_context_batch_encode_host(astc_b200_context *ctx, const astc_b200_
                 ++i;
             }
             g.count = i - g.first;
+            bool any_in = false, any_out = false;
             for (size_t k = g.first; k < i; ++k) {
                 const Item &it = items[k];
                 table[k] = make_desc(nullptr, nullptr, it.in_pitch, it.im->width, it.im->height, d, g.blocks);   // pointers filled in below
                 g.blocks += it.blocks;
                 g.out_bytes += it.out_bytes;
+                any_in |= it.via_in;
+                any_out |= it.via_out;
             }
+            g.in_span = items[i - 1].in_off + items[i - 1].in_bytes - g.in_off;
+            if (any_in) slot_in = std::max(slot_in, align_up(g.in_span, 256));
+            if (any_out) slot_out = std::max(slot_out, align_up(g.out_bytes, 256));
             groups.push_back(g);
         }
     } catch (const std::bad_alloc &) {
@@ -327,8 +433,8 @@ int astc_b200_context_batch_encode_host(astc_b200_context *ctx, const astc_b200_
     CUDA_TRY(reserve_device(ctx->d_in, in_total));
     CUDA_TRY(reserve_device(ctx->d_out, out_total));
     CUDA_TRY(reserve_device(ctx->d_table, table.size()));
-    CUDA_TRY(reserve_pinned(ctx->h_stage_in, stage_in_total));
-    CUDA_TRY(reserve_pinned(ctx->h_stage_out, stage_out_total));
+    CUDA_TRY(reserve_pinned(ctx->h_stage_in, slot_in * kStreams));
+    CUDA_TRY(reserve_pinned(ctx->h_stage_out, slot_out * kStreams));
     for (size_t k = 0; k < items.size(); ++k) {
         table[k].rgba = ctx->d_in.ptr + items[k].in_off;
         table[k].blocks = ctx->d_out.ptr + items[k].out_off;
@@ -339,67 +445,80 @@ int astc_b200_context_batch_encode_host(astc_b200_context *ctx, const astc_b200_
     if (err == cudaSuccess) err = cudaEventRecord(ctx->ready, ctx->streams[0]);
     for (int s = 1; s < kStreams && err == cudaSuccess; ++s) err = cudaStreamWaitEvent(ctx->streams[s], ctx->ready, 0);
 
-    // ---- per group: uploads, one launch, downloads; groups rotate over the streams ----
+    // group gi is complete: its slot outputs go to the callers' buffers (the slot is free again afterwards)
+    auto retire = [&](size_t gi) -> cudaError_t {
+        const Group &g = groups[gi];
+        const int s = int(gi % kStreams);
+        const cudaError_t e = cudaEventSynchronize(ctx->slot_done[s]);
+        if (e != cudaSuccess) return e;
+        const uint8_t *slot = ctx->h_stage_out.ptr + size_t(s) * slot_out;
+        for (size_t k = g.first; k < g.first + g.count; ++k) {
+            const Item &it = items[k];
+            if (it.via_out) ctx->pool.copy_rows(it.im->h_blocks, it.out_bytes, slot + (it.out_off - g.out_off), it.out_bytes, it.out_bytes, 1);
+        }
+        return cudaSuccess;
+    };
+
+    // ---- per group: slot fill + uploads, one launch, downloads; groups rotate over the streams and the slots ----
+    size_t retired = 0;
     for (size_t gi = 0; gi < groups.size() && err == cudaSuccess; ++gi) {
         const Group &g = groups[gi];
-        cudaStream_t st = ctx->streams[gi % kStreams];
-        // small sources: gathered on the host into pinned staging (densely, at the image's device pitch), runs of
-        // consecutive small images uploaded with ONE copy each
+        const int s = int(gi % kStreams);
+        cudaStream_t st = ctx->streams[s];
+        if (gi >= size_t(kStreams)) { err = retire(gi - kStreams); ++retired; if (err != cudaSuccess) break; }
+        uint8_t *slot = ctx->h_stage_in.ptr + size_t(s) * slot_in;
         size_t k = g.first;
         const size_t end = g.first + g.count;
         while (k < end && err == cudaSuccess) {
             const Item &it = items[k];
-            if (!it.small_in) {
+            if (!it.via_in) {
                 err = upload_rows(ctx->d_in.ptr + it.in_off, it.in_pitch, it.im->h_rgba, it.im->pitch_bytes,
                                   size_t(it.im->width) * 4u, size_t(it.im->height), st);
                 ++k;
                 continue;
             }
-            // a run of small images: consecutive in the batch, hence consecutive -- with the same 256-byte padding --
-            // in the arena and in the staging buffer: gathered by the host, uploaded with one copy
+            // a run of slot images: consecutive in the batch, hence consecutive -- with the same 256-byte padding --
+            // in the arena and in the slot: gathered by the host (workers for the large ones), uploaded with one copy
             size_t run_end = k;
-            while (run_end < end && items[run_end].small_in) ++run_end;
-            for (size_t j = k; j < run_end; ++j) {
-                const Item &sj = items[j];
-                uint8_t *dst = ctx->h_stage_in.ptr + sj.stage_in;
-                const size_t row = size_t(sj.im->width) * 4u;
-                for (int y = 0; y < sj.im->height; ++y)
-                    std::memcpy(dst + size_t(y) * sj.in_pitch, sj.im->h_rgba + size_t(y) * sj.im->pitch_bytes, row);
+            for (; run_end < end && items[run_end].via_in; ++run_end) {
+                const Item &sj = items[run_end];
+                ctx->pool.copy_rows(slot + (sj.in_off - g.in_off), sj.in_pitch, sj.im->h_rgba, sj.im->pitch_bytes,
+                                    size_t(sj.im->width) * 4u, size_t(sj.im->height), /*streaming=*/sj.in_bytes >= kSmallImage);
             }
             const Item &last = items[run_end - 1];
-            err = cudaMemcpyAsync(ctx->d_in.ptr + it.in_off, ctx->h_stage_in.ptr + it.stage_in, last.in_off + last.in_bytes - it.in_off,
+            err = cudaMemcpyAsync(ctx->d_in.ptr + it.in_off, slot + (it.in_off - g.in_off), last.in_off + last.in_bytes - it.in_off,
                                   cudaMemcpyHostToDevice, st);
             k = run_end;
         }
         if (err != cudaSuccess) break;
         astc::EncodeParams p{};
-        p.single = table[g.table_first];
-        p.table = g.count > 1 ? ctx->d_table.ptr + g.table_first : nullptr;
+        p.single = table[g.first];
+        p.table = g.count > 1 ? ctx->d_table.ptr + g.first : nullptr;
         p.count = int(g.count);
         p.total_blocks = g.blocks;
         err = astc::launch_encode(d, opt->has_alpha != 0, opt->is_normal_map != 0, opt->srgb != 0, opt->axis_method, p, st);
         if (err != cudaSuccess) break;
         astc_capi::count_launch();
-        // outputs: large ones straight to the caller's buffer; the small ones of the group lie contiguously in the
-        // arena between them, so each run of small outputs is ONE copy into pinned staging, scattered after the sync
+        // outputs: large pinned ones straight to the caller's buffer; each run of slot outputs is ONE copy into the slot
+        uint8_t *oslot = ctx->h_stage_out.ptr + size_t(s) * slot_out;
         k = g.first;
         while (k < end && err == cudaSuccess) {
             const Item &it = items[k];
-            if (!it.small_out) {
+            if (!it.via_out) {
                 err = cudaMemcpyAsync(it.im->h_blocks, ctx->d_out.ptr + it.out_off, it.out_bytes, cudaMemcpyDeviceToHost, st);
                 ++k;
                 continue;
             }
             size_t run_end = k, bytes = 0;
-            while (run_end < end && items[run_end].small_out) { bytes += items[run_end].out_bytes; ++run_end; }
-            err = cudaMemcpyAsync(ctx->h_stage_out.ptr + it.stage_out, ctx->d_out.ptr + it.out_off, bytes, cudaMemcpyDeviceToHost, st);
+            while (run_end < end && items[run_end].via_out) { bytes += items[run_end].out_bytes; ++run_end; }
+            err = cudaMemcpyAsync(oslot + (it.out_off - g.out_off), ctx->d_out.ptr + it.out_off, bytes, cudaMemcpyDeviceToHost, st);
             k = run_end;
         }
+        if (err == cudaSuccess) err = cudaEventRecord(ctx->slot_done[s], st);
     }
+    for (size_t gi = retired; gi < groups.size() && err == cudaSuccess; ++gi) err = retire(gi);
     err = sync_all(ctx, err);
     if (err != cudaSuccess) return cuda_fail(err, "astc_b200_context_batch_encode_host");
-    for (const Item &it : items)
-        if (it.small_out) std::memcpy(it.im->h_blocks, ctx->h_stage_out.ptr + it.stage_out, it.out_bytes);
     return ASTC_B200_OK;
 }
 

@@ -114,7 +114,8 @@ ASTC_B200_API int astc_b200_encode_device(const uint8_t *d_rgba, int width, int 
 
 /* load_tex upload + encode_astc + read_gpu in one synchronous call on host
  * buffers: banded H2D copy / kernel / D2H copy pipelined over internal
- * streams.  Pinned host memory (astc_b200_host_alloc) gives full PCIe rate. */
+ * streams.  Pinned host memory (astc_b200_host_alloc) gives full PCIe rate;
+ * pageable memory is staged through pinned slots by worker threads.        */
 ASTC_B200_API int astc_b200_encode_host(const uint8_t *h_rgba, int width, int height,
                                         size_t pitch_bytes, const astc_b200_option *opt,
                                         uint8_t *h_blocks);
@@ -129,6 +130,11 @@ typedef struct astc_b200_context astc_b200_context;
 ASTC_B200_API int astc_b200_context_create(astc_b200_context **ctx);
 ASTC_B200_API void astc_b200_context_destroy(astc_b200_context *ctx);
 ASTC_B200_API int astc_b200_context_trim(astc_b200_context *ctx);     /* give the workspace back; it regrows on demand */
+/* PAGEABLE host buffers (malloc / new[] / stbi_load -- what main.cpp:24,224 holds) of 1 MiB or more take a staged
+ * pipeline: worker threads copy each band into pinned slots while the bands before it are on the link and on the SMs
+ * (2-3x the driver's own pageable staging).  `threads` = workers besides the caller: -1 automatic (a quarter of the
+ * host's hardware threads, 1..7; the default), 0 none.  Call between encodes. */
+ASTC_B200_API int astc_b200_context_set_copy_threads(astc_b200_context *ctx, int threads);
 ASTC_B200_API int astc_b200_context_encode_host(astc_b200_context *ctx, const uint8_t *h_rgba, int width,
                                                 int height, size_t pitch_bytes,
                                                 const astc_b200_option *opt, uint8_t *h_blocks);

@@ -92,6 +92,21 @@ def test_batch_encode_host_pinned_and_errors(native):
     a = ctx.batch_encode_host([pinned.numpy()], opt)[0]
     b = ctx.encode_host(src.numpy(), opt)
     assert np.array_equal(a, b)
+    # pinned and pageable, large and small, mixed in one batch -- and more groups than there are slots (3)
+    mixed, want = [], []
+    for i in range(14):
+        size = (1536, 96, 2048, 40)[i % 4]
+        t = synth.synth_rgba(size, size + 8 * i, 30 + i)
+        if i % 3 == 0:
+            p = torch.empty(t.shape, dtype=torch.uint8, pin_memory=True)
+            p.copy_(t)
+            mixed.append(p.numpy())
+        else:
+            mixed.append(t.numpy())
+        want.append(_device_encode(native, t.numpy(), opt))
+    outs = [torch.empty(w.shape, dtype=torch.uint8, pin_memory=True).numpy() if i % 2 else np.empty_like(w) for i, w in enumerate(want)]
+    ctx.batch_encode_host(mixed, opt, outs=outs)
+    assert all(np.array_equal(o, w) for o, w in zip(outs, want))
     L = native.lib()
     o = opt._abi()
     assert L.astc_b200_context_encode_host(None, src.numpy().ctypes.data, 8, 8, 32, C.byref(o), a.ctypes.data) == -1
@@ -99,4 +114,39 @@ def test_batch_encode_host_pinned_and_errors(native):
     assert L.astc_b200_context_batch_encode_host(ctx._h, None, 3, C.byref(o)) == -1
     bad = opt._abi(); bad.axis_method = 7
     assert L.astc_b200_context_encode_host(ctx._h, src.numpy().ctypes.data, 8, 8, 32, C.byref(bad), a.ctypes.data) == -1
+    ctx.close()
+
+
+@pytest.mark.parametrize("dim", [4, 6])
+def test_staged_pipeline_for_pageable_memory(native, dim):
+    """Pageable (numpy) sources / destinations of >= 1 MiB go through the staged pipeline (worker threads copy bands
+    into pinned slots): many bands, ragged last band, rows that are not a multiple of 16 bytes (padded device pitch),
+    strided host rows, pinned-in / pageable-out and the reverse -- always the device path's bytes."""
+    import torch
+    from astc_encoder_b200 import synth
+    ctx = native.Context()
+    opt = native.encode_option(is4x4=dim == 4, is6x6=dim == 6, has_alpha=True)
+    for (w, h) in ((4096, 4096), (1021, 1537), (2048, 130), (8192, 33), (515, 515)):
+        img = synth.synth_rgba(w, h, 500 + w + h).numpy()
+        want = _device_encode(native, img, opt)
+        assert np.array_equal(ctx.encode_host(img, opt), want), (w, h)
+        assert np.array_equal(native.encode_astc_host(img, opt), want), (w, h)            # default context
+    img = synth.synth_rgba(3000, 1111, 9).numpy()
+    want = _device_encode(native, img, opt)
+    for threads in (0, 1, 6, -1):                                        # caller only ... automatic
+        ctx.set_copy_threads(threads)
+        assert np.array_equal(ctx.encode_host(img, opt), want), threads
+    assert native.lib().astc_b200_context_set_copy_threads(ctx._h, 1000) == -1
+    wide = synth.synth_rgba(1100, 700, 3).numpy()
+    view = wide[:, 37:1061]                                              # pitch > 4 * width, pageable
+    assert np.array_equal(ctx.encode_host(view, opt), _device_encode(native, view, opt))
+    # pinned in, pageable out -- and pageable in, pinned out
+    src = synth.synth_rgba(2048, 1024, 8)
+    pin = torch.empty((1024, 2048, 4), dtype=torch.uint8, pin_memory=True)
+    pin.copy_(src)
+    want = _device_encode(native, src.numpy(), opt)
+    assert np.array_equal(ctx.encode_host(pin.numpy(), opt), want)
+    out_pin = torch.empty(want.shape, dtype=torch.uint8, pin_memory=True)
+    ctx.encode_host(src.numpy(), opt, out=out_pin.numpy())
+    assert np.array_equal(out_pin.numpy(), want)
     ctx.close()

@@ -160,3 +160,13 @@ def test_cli_reproduces_readme_example(native, oracle, tmp_path, leaf_golden):
     assert (xd, yd) == (6, 6) and len(blocks) == 171 * 171
     want = oracle.encode_image(native.load_image(str(src), True), block_dim=6, srgb=True)
     assert np.array_equal(blocks, want)
+
+
+def test_copy_pool_unit(tmp_path):
+    """The worker pool behind the staged (pageable-memory) pipeline of astc_b200_context_encode_host, compiled as plain
+    C++ and run on the CPU: pitched / contiguous / tiny / multi-grain jobs against memcpy row by row."""
+    exe = tmp_path / "copy_pool_test"
+    subprocess.run(["g++", "-std=c++17", "-O2", "-pthread", "-I", str(ROOT / "astc_encoder_b200" / "csrc"),
+                    str(ROOT / "tests" / "cpp" / "copy_pool_test.cpp"), "-o", str(exe)], check=True)
+    res = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0 and "copy_pool_test: ok" in res.stdout, res.stdout + res.stderr
