@@ -24,12 +24,25 @@ struct ImageDesc {
     uint32_t flags;
 };
 
+// CTAs [cta_begin, cta_end) encode `passes` runs of blockDim.x consecutive block ids each, starting at first_block.
+// A launch is a few segments with shrinking pass counts (set by launch_encode): long CTAs first, short ones last, so
+// that the SMs run out of work within one short CTA of each other instead of one long one.
+struct Segment {
+    uint64_t first_block;
+    uint32_t cta_begin, cta_end;
+    uint32_t passes;
+    uint32_t pad;
+};
+constexpr int kMaxSegments = 4;
+
 struct EncodeParams {
     ImageDesc single;            // used when table == nullptr
     const ImageDesc *table;      // device array, sorted by first_block
     int32_t count;
     uint64_t total_blocks;
     int32_t passes;              // blocks each thread encodes one after the other (set by launch_encode)
+    int32_t nseg;                // 0: every CTA runs `passes` passes
+    Segment seg[kMaxSegments];
 };
 
 // axis_method: 0 = PCA power iteration (the reference's shipped path), 1 = max_accumulation_pixel_direction

@@ -170,3 +170,13 @@ def test_copy_pool_unit(tmp_path):
                     str(ROOT / "tests" / "cpp" / "copy_pool_test.cpp"), "-o", str(exe)], check=True)
     res = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert res.returncode == 0 and "copy_pool_test: ok" in res.stdout, res.stdout + res.stderr
+
+
+def test_cta_schedule_unit(tmp_path):
+    """The launch schedule (csrc/astc_schedule.h): uniform and tapered plans cover every block id exactly once."""
+    cuda_inc = "/usr/local/cuda/include"
+    exe = tmp_path / "schedule_test"
+    subprocess.run(["g++", "-std=c++17", "-O2", "-I", str(ROOT / "astc_encoder_b200" / "csrc"), "-I", cuda_inc,
+                    str(ROOT / "tests" / "cpp" / "schedule_test.cpp"), "-o", str(exe)], check=True)
+    res = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0 and "schedule_test: ok" in res.stdout, res.stdout + res.stderr
