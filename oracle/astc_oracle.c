@@ -359,6 +359,8 @@ static const int8_t *g_rcp_delta = NULL, *g_rsq_delta = NULL;
 static unsigned g_variant = 0;           /* sensitivity switches, tools/pin_sensitivity.py only */
 
 void astc_oracle_set_variant(unsigned flags) { g_variant = flags; }
+static int g_rcp_bias = 0, g_rsq_bias = 0;  /* ulps added to every rcp / rsq result, tools/golden_residual.py only */
+void astc_oracle_set_mufu_bias(int rcp_ulps, int rsq_ulps) { g_rcp_bias = rcp_ulps; g_rsq_bias = rsq_ulps; }
 
 void astc_oracle_set_mufu_tables(const int8_t *rcp_delta, const int8_t *rsq_delta)
 {
@@ -375,7 +377,7 @@ float astc_oracle_mufu_rcp(float x)
     const float base = (float)(1.0 / (double)x);
     if (g_variant & ASTC_ORACLE_VAR_EXACT_RCP_RSQ) return base;
     if (!g_rcp_delta) return u2f(0x7FC00000u);                 /* tables not loaded: poison, never a silent fallback */
-    return u2f(f2u(base) + (uint32_t)(int32_t)g_rcp_delta[b & 0x7FFFFFu]);
+    return u2f(f2u(base) + (uint32_t)(int32_t)g_rcp_delta[b & 0x7FFFFFu] + (uint32_t)g_rcp_bias);
 }
 
 float astc_oracle_mufu_rsq(float x)
@@ -384,7 +386,7 @@ float astc_oracle_mufu_rsq(float x)
     const float base = (float)(1.0 / sqrt((double)x));
     if (g_variant & ASTC_ORACLE_VAR_EXACT_RCP_RSQ) return base;
     if (!g_rsq_delta) return u2f(0x7FC00000u);
-    return u2f(f2u(base) + (uint32_t)(int32_t)g_rsq_delta[(parity << 23) | (b & 0x7FFFFFu)]);
+    return u2f(f2u(base) + (uint32_t)(int32_t)g_rsq_delta[(parity << 23) | (b & 0x7FFFFFu)] + (uint32_t)g_rsq_bias);
 }
 
 /* eigen_vector (ASTC_Encode.hlsl:93-106): power iteration, two mat-vecs per

@@ -73,6 +73,10 @@ enum {
     ASTC_ORACLE_VAR_UNFUSED_DEV = 16     /* texel*255 rounded before the subtraction of mean / e0 (no FMA)             */
 };
 void astc_oracle_set_variant(unsigned flags);
+/* tools/golden_residual.py ONLY: adds the given number of ulps to EVERY result of the emulated MUFU.RCP / MUFU.RSQ
+ * (0, 0 = the units as captured).  Answers "would the golden's bits follow if the reciprocal unit of the GPU that
+ * made it differed from the B200's in the last bit for this argument?" for the residual blocks. */
+void astc_oracle_set_mufu_bias(int rcp_ulps, int rsq_ulps);
 
 /* Diagnostics of one block encode (unrounded endpoints, raw weights). */
 typedef struct astc_oracle_trace {

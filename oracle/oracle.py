@@ -142,6 +142,11 @@ def make_opt(block_dim=4, has_alpha=False, is_normal_map=False, srgb=False, axis
 VAR_TRUE_DIVISION, VAR_UNFUSED_SAMPLE, VAR_SRGB_POWF, VAR_EXACT_RCP_RSQ, VAR_UNFUSED_DEV = 1, 2, 4, 8, 16
 
 
+def set_mufu_bias(rcp_ulps: int, rsq_ulps: int) -> None:
+    """tools/golden_residual.py only: ulps added to every emulated rcp / rsq result (0, 0 = as captured).  Process-wide."""
+    lib().astc_oracle_set_mufu_bias(int(rcp_ulps), int(rsq_ulps))
+
+
 def set_variant(flags: int) -> None:
     """Sensitivity switches of tools/pin_sensitivity.py (0 = canonical arithmetic).  Process-wide."""
     lib().astc_oracle_set_variant(int(flags))

@@ -138,3 +138,7 @@ def test_residual_blocks_are_the_committed_list(oracle, encoded, leaf_golden):
     assert sum(r["closest_weight_to_a_half"] <= 3e-7 for r in by_class["weights+-1"]) >= 23
     # swap ties: the rounded rgb sums of the two endpoints are EQUAL here, so `>` (:127) hangs on the last bit
     assert all(r["rounded_rgb_sum_e1_minus_e0"] == 0.0 for r in by_class["endpoint_swap_tie"])
+    # 23 of the 25 weight-only blocks take the golden's bits when every rcp / rsq result is moved by one ulp
+    # (oracle.set_mufu_bias; the units are specified to ~1 ulp and the golden's GPU is unknown)
+    assert sum(bool(r["reproduced_with_mufu_result_moved_by_one_ulp"]) for r in by_class["weights+-1"]) == 23
+    assert not any(r["reproduced_with_mufu_result_moved_by_one_ulp"] for c, rs in by_class.items() if c != "weights+-1" for r in rs)
