@@ -233,25 +233,57 @@ __device__ __forceinline__ uint64_t cta_schedule(const EncodeParams &p, uint32_t
     return first + uint64_t(blockIdx.x - begin) * uint32_t(q * threads);
 }
 
-template <bool ALPHA, bool SRGB, bool UNORM_LUT>
-__device__ __forceinline__ void load_shared_tables(dev::SharedTables &st)
+// The per-CTA tables (immutable module globals) travel global -> registers -> shared memory in two steps, so that
+// other start-up work can be issued while the loads are in flight: one 16-byte piece per thread and table.
+struct TableRegs {
+    uint4 pack, lut, lut_a;
+};
+template <bool ALPHA, bool SRGB, bool UNORM_LUT, bool ALPHA_LUT>
+__device__ __forceinline__ TableRegs fetch_tables()
 {
     static_assert(sizeof(dev::TableImage) % 16 == 0 && offsetof(dev::SharedTables, lut_rgb) == sizeof(dev::TableImage), "table layout");
-    const uint4 *src = reinterpret_cast<const uint4 *>(ALPHA ? &g_tables_q6 : &g_tables_q12);
-    uint4 *dst = reinterpret_cast<uint4 *>(&st);
-    for (int i = threadIdx.x; i < int(sizeof(dev::TableImage) / 16); i += blockDim.x) dst[i] = __ldg(src + i);
-    if (SRGB || UNORM_LUT) {
-        const uint4 *lsrc = reinterpret_cast<const uint4 *>(SRGB ? &g_srgb_lut : &g_unorm_lut);
-        uint4 *ldst = reinterpret_cast<uint4 *>(st.lut_rgb);
-        for (int i = threadIdx.x; i < 64; i += blockDim.x) ldst[i] = __ldg(lsrc + i);
-    }
+    constexpr int kPieces = int(sizeof(dev::TableImage) / 16);
+    static_assert(kPieces <= 128, "one piece per thread of a 128-thread CTA");
+    TableRegs r{};
+    const int i = threadIdx.x;
+    if (i < kPieces) r.pack = __ldg(reinterpret_cast<const uint4 *>(ALPHA ? &g_tables_q6 : &g_tables_q12) + i);
+    if ((SRGB || UNORM_LUT) && i < 64) r.lut = __ldg(reinterpret_cast<const uint4 *>(SRGB ? &g_srgb_lut : &g_unorm_lut) + i);
+    if (ALPHA_LUT && i >= 64 && i < 128) r.lut_a = __ldg(reinterpret_cast<const uint4 *>(&g_unorm_lut) + (i - 64));
+    return r;
+}
+template <bool SRGB, bool UNORM_LUT, bool ALPHA_LUT>
+__device__ __forceinline__ void store_tables(dev::SharedTables &st, float *lut_a, const TableRegs &r)
+{
+    constexpr int kPieces = int(sizeof(dev::TableImage) / 16);
+    const int i = threadIdx.x;
+    if (i < kPieces) reinterpret_cast<uint4 *>(&st)[i] = r.pack;
+    if ((SRGB || UNORM_LUT) && i < 64) reinterpret_cast<uint4 *>(st.lut_rgb)[i] = r.lut;
+    if (ALPHA_LUT && i >= 64 && i < 128) reinterpret_cast<uint4 *>(lut_a)[i - 64] = r.lut_a;
 }
 
-__device__ __forceinline__ void load_alpha_lut(float *lut_a)
+// Programmatic dependent launch (sm_90+).  The encode kernels are launched with the programmatic-stream-serialization
+// attribute: a launch may become resident while the kernel before it in the stream is still draining.  Everything a
+// CTA does before pdl_wait() touches only kernel parameters and immutable module globals (the table fetch above);
+// pdl_wait() returns once the preceding grid has completed and its memory is visible, so every read of the source
+// texture, of the batch's descriptor table and every store comes after it.  pdl_trigger() lets the NEXT launch start
+// filling SM slots as soon as all CTAs of this one have been dispatched.  Both are no-ops in an ordinary launch.
+// Measured on B200 (round 2q, same-box A/B over back-to-back launches, profiles/r2q_ab_pdl.txt): 2048^2 16.6 -> 14.5 us
+// per launch, 4096^2 49.6 -> 47.0, 1/8 band of 16384^2 91.1 -> 89.1, 16384^2 682.2 -> 680.5; isolated launches unchanged.
+// -DASTC_PDL=0 builds plain launches.
+#ifndef ASTC_PDL
+#define ASTC_PDL 1
+#endif
+__device__ __forceinline__ void pdl_trigger()
 {
-    const uint4 *asrc = reinterpret_cast<const uint4 *>(&g_unorm_lut);
-    uint4 *adst = reinterpret_cast<uint4 *>(lut_a);
-    for (int i = threadIdx.x; i < 64; i += blockDim.x) adst[i] = __ldg(asrc + i);
+#if ASTC_PDL
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_wait()
+{
+#if ASTC_PDL
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
 }
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return uint32_t(__cvta_generic_to_shared(p)); }
@@ -317,15 +349,17 @@ encode4x4_kernel(const EncodeParams p)
 
     // CTA b owns ids [b*BPT*T, (b+1)*BPT*T); pass i takes the i-th run of T consecutive ids, so a
     // warp reads 512 contiguous bytes per texel row and stores 512 contiguous bytes.
-    // The first block's rows are requested BEFORE the tables are fetched: the two HBM / L2 round trips of a
-    // CTA's start-up then overlap instead of following each other (the landing slots do not alias the tables).
+    // The tables are requested (into registers), then the first block's rows (cp.async), and only then are the tables
+    // stored to shared memory: the two HBM / L2 round trips of a CTA's start-up overlap instead of following each other.
+    pdl_trigger();
+    const TableRegs tables = fetch_tables<ALPHA, SRGB, true, SRGB>();      // in flight while the first rows are requested
+    pdl_wait();
     Walk<BATCH> wk;
     int passes;
     const uint64_t cta_first = cta_schedule(p, kThreads4x4, passes);
     const bool any = wk.start(p, cta_first + threadIdx.x);
     bool fast = any && prefetch_rows4x4<BATCH>(p, wk, slot0);
-    load_shared_tables<ALPHA, SRGB, true>(st);
-    if (SRGB) load_alpha_lut(s_lut_a);
+    store_tables<SRGB, true, SRGB>(st, s_lut_a, tables);
     __syncthreads();
     if (!any) return;
     const uint32_t s_field = smem_addr(st.field), s_trit = smem_addr(st.trit_scattered);
@@ -446,6 +480,9 @@ encode6x6_kernel(const EncodeParams p)
     // each of its blocks (only it reads or writes that column: no barrier between passes).
     // The first block's rows are pulled towards L2 before the tables are fetched, so that the two round trips of
     // a CTA's start-up overlap.
+    pdl_trigger();
+    const TableRegs tables = fetch_tables<ALPHA, SRGB, false, false>();
+    pdl_wait();
     Walk<BATCH> wk;
     int passes;
     const uint64_t cta_first = cta_schedule(p, kThreads6x6, passes);
@@ -458,7 +495,7 @@ encode6x6_kernel(const EncodeParams p)
             for (int r = 0; r < 6; ++r) asm volatile("prefetch.global.L2 [%0];" ::"l"(b0 + size_t(r) * d0.pitch));
         }
     }
-    load_shared_tables<ALPHA, SRGB, false>(st);
+    store_tables<SRGB, false, false>(st, nullptr, tables);
     __syncthreads();
     if (!any) return;
     const uint32_t s_field = smem_addr(st.field), s_trit = smem_addr(st.trit_scattered);
@@ -553,6 +590,27 @@ static uint64_t plan_schedule(EncodeParams &p, int threads, int ctas_per_sm)
     return plan_tapered(p, threads, uint64_t(sm_count) * uint64_t(ctas_per_sm), ASTC_TAPER != 0);
 }
 
+template <typename K>
+static cudaError_t launch_pdl(K kern, unsigned ctas, int threads, size_t smem, cudaStream_t stream, const EncodeParams &p)
+{
+#if ASTC_PDL
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(ctas);
+    cfg.blockDim = dim3(unsigned(threads));
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, p);
+#else
+    kern<<<ctas, threads, smem, stream>>>(p);
+    return cudaGetLastError();
+#endif
+}
+
 template <bool ALPHA, bool NORMAL, bool SRGB, bool BATCH, bool ACCUM>
 static cudaError_t launch_variant(int dim, EncodeParams p, cudaStream_t stream)
 {
@@ -560,7 +618,7 @@ static cudaError_t launch_variant(int dim, EncodeParams p, cudaStream_t stream)
         p.passes = choose_passes(p.total_blocks, kThreads4x4, NORMAL ? ASTC_MINBLOCKS_4X4_NORMAL : ASTC_MINBLOCKS_4X4, kMaxPasses);
         const uint64_t ctas = plan_schedule(p, kThreads4x4, NORMAL ? ASTC_MINBLOCKS_4X4_NORMAL : ASTC_MINBLOCKS_4X4);
         if (ctas > 0x7FFFFFFFull) return cudaErrorInvalidConfiguration;
-        encode4x4_kernel<ALPHA, NORMAL, SRGB, BATCH, ACCUM><<<unsigned(ctas), kThreads4x4, 0, stream>>>(p);
+        return launch_pdl(encode4x4_kernel<ALPHA, NORMAL, SRGB, BATCH, ACCUM>, unsigned(ctas), kThreads4x4, 0, stream, p);
     } else {
         auto kern = encode6x6_kernel<ALPHA, NORMAL, SRGB, BATCH, ACCUM>;
         constexpr size_t kSmem6x6 = smem6x6<NORMAL>();
@@ -576,9 +634,8 @@ static cudaError_t launch_variant(int dim, EncodeParams p, cudaStream_t stream)
             if (e != cudaSuccess) return e;
             configured_device = devno;
         }
-        kern<<<unsigned(ctas), kThreads6x6, kSmem6x6, stream>>>(p);
+        return launch_pdl(kern, unsigned(ctas), kThreads6x6, kSmem6x6, stream, p);
     }
-    return cudaGetLastError();
 }
 
 template <bool BATCH, bool ACCUM>
