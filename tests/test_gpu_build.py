@@ -44,6 +44,10 @@ def _probe(lib_path=None):
 
 def test_library_builds_from_source_on_this_box():
     from astc_encoder_b200 import build as B
+    try:
+        B._nvcc()
+    except RuntimeError as e:                              # a GPU box without the CUDA toolkit: nothing to prove here
+        pytest.skip(str(e))
     lib = B.build_variant("boxbuild", [])               # every .cu / .cpp through nvcc -gencode arch=compute_100a,code=sm_100a
     try:
         assert lib.exists() and lib.stat().st_size > 1_000_000
