@@ -267,3 +267,26 @@ def test_batch_and_decode_reject_malformed_tensors(native):
         native.decode_astc(torch.zeros((3, 16), dtype=torch.uint8, device="cuda"), 16, 16, 4)              # 16 blocks needed
     with pytest.raises(ValueError):
         native.decode_astc(torch.zeros((16, 16), dtype=torch.uint8, device="cuda"), 16, 16, 5)
+
+
+@pytest.mark.parametrize("dim", [4, 6])
+def test_tapered_schedule_in_a_ragged_batch(native, dim):
+    """A batch large enough for the tapered schedule (CTAs of 8, 4, 2 and 1 passes, csrc/astc_schedule.h), made of
+    ragged textures, so that segment boundaries fall inside images, inside block rows and between images: the one
+    launch must give each texture the bytes of its own single-texture encode (which runs the uniform schedule for
+    the small ones and a differently cut tapered one for the large ones)."""
+    import torch
+    from astc_encoder_b200 import synth
+    rng = np.random.default_rng(2024 + dim)
+    opt = native.encode_option(is4x4=dim == 4, is6x6=dim == 6, has_alpha=True)
+    srcs = []
+    for i in range(36):
+        w, h = (int(rng.integers(600, 1500)), int(rng.integers(600, 1500))) if i % 6 else (int(rng.integers(1, 40)), int(rng.integers(1, 40)))
+        srcs.append(synth.synth_rgba(w, h, 900 + i, device="cuda"))
+    batch = native.Batch(srcs, opt)
+    assert batch.total_blocks > 592 * 15 * 128 * (1 if dim == 4 else 0.2)
+    batch.encode()
+    torch.cuda.synchronize()
+    for s, o in zip(srcs, batch.outputs):
+        assert torch.equal(o, native.encode_astc(s, opt)), tuple(s.shape)
+    batch.close()
