@@ -201,7 +201,15 @@ struct Walk {
             divide(__ldg(&p.table[idx].blocks_x));
         } else {
             const uint32_t blocks_x = BATCH ? __ldg(&p.table[idx].blocks_x) : p.single.blocks_x;
+#ifdef ASTC_WALK_DIVIDE_ALWAYS
             if (bx >= blocks_x) divide(blocks_x);
+#else
+            if (bx >= blocks_x) {                              // crossed the end of a block row: usually into the next one
+                bx -= blocks_x;
+                ++by;
+                if (bx >= blocks_x) divide(blocks_x);          // rows shorter than the stride
+            }
+#endif
         }
         return true;
     }
