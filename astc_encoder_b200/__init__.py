@@ -26,7 +26,7 @@ import numpy as np
 __all__ = [
     "encode_option", "AstcError", "lib", "block_dim", "block_counts", "output_size", "band",
     "encode_astc", "encode_astc_host", "read_gpu", "save_astc", "save_astc_slice", "load_astc", "load_image", "load_tex",
-    "decode_astc", "downsample2x2", "mip_chain", "mufu", "bise_encode", "Batch", "Context", "launch_count", "unorm_lut", "version",
+    "decode_astc", "downsample2x2", "mip_chain", "mip_chain_layout", "mip_chain_by_level", "mufu", "bise_encode", "Batch", "Context", "launch_count", "unorm_lut", "version",
 ]
 
 _PKG = Path(__file__).resolve().parent
@@ -120,6 +120,9 @@ _SIGNATURES = {
     "astc_b200_context_create": (C.c_int, [C.POINTER(C.c_void_p)]),
     "astc_b200_context_destroy": (None, [C.c_void_p]),
     "astc_b200_context_trim": (C.c_int, [C.c_void_p]),
+    "astc_b200_mip_chain_layout": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_size_t), C.POINTER(C.c_int),
+                                             C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
+    "astc_b200_mip_chain_device": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
     "astc_b200_context_set_copy_threads": (C.c_int, [C.c_void_p, C.c_int]),
     "astc_b200_context_encode_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.POINTER(_Option), C.c_void_p]),
     "astc_b200_context_batch_encode_host": (C.c_int, [C.c_void_p, C.POINTER(_HostImage), C.c_int, C.POINTER(_Option)]),
@@ -446,8 +449,34 @@ def downsample2x2(img, out=None, stream=None):
     return out
 
 
-def mip_chain(base, stream=None):
-    """[base, level 1, ..., 1x1] generated on the device, one launch per level."""
+def mip_chain_layout(width: int, height: int):
+    """(offsets, widths, heights, total_bytes) of the levels below a width x height base in one arena
+    (astc_b200_mip_chain_layout)."""
+    n, total = C.c_int(), C.c_size_t()
+    offs, ws, hs = (C.c_size_t * 24)(), (C.c_int * 24)(), (C.c_int * 24)()
+    _check(lib().astc_b200_mip_chain_layout(int(width), int(height), C.byref(n), offs, ws, hs, C.byref(total)), "mip_chain_layout")
+    return list(offs[:n.value]), list(ws[:n.value]), list(hs[:n.value]), int(total.value)
+
+
+def mip_chain(base, stream=None, arena=None):
+    """[base, level 1, ..., 1x1] generated on the device by ONE call (astc_b200_mip_chain_device: one fused launch
+    when both sides are multiples of 64, else one launch per level).  The levels are views into one arena tensor."""
+    import torch
+    h, w, pitch = _check_src(base)
+    offs, ws, hs, total = mip_chain_layout(w, h)
+    if not offs:
+        return [base]
+    if arena is None:
+        arena = torch.empty(total, dtype=torch.uint8, device=base.device)
+    elif not (arena.is_cuda and arena.dtype == torch.uint8 and arena.is_contiguous() and arena.numel() >= total and arena.device == base.device):
+        raise ValueError("arena must be a contiguous CUDA uint8 tensor of at least mip_chain_layout's total_bytes on the base's device")
+    with torch.cuda.device(base.device):
+        _check(lib().astc_b200_mip_chain_device(base.data_ptr(), w, h, pitch, arena.data_ptr(), arena.numel(), _stream_ptr(stream)), "mip_chain")
+    return [base] + [arena[o:o + lw * lh * 4].view(lh, lw, 4) for o, lw, lh in zip(offs, ws, hs)]
+
+
+def mip_chain_by_level(base, stream=None):
+    """The same chain, one astc_b200_downsample2x2_device launch per level (the checker of mip_chain)."""
     chain = [base]
     while chain[-1].shape[0] > 1 or chain[-1].shape[1] > 1:
         chain.append(downsample2x2(chain[-1], stream=stream))

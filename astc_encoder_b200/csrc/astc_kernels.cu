@@ -907,6 +907,122 @@ cudaError_t launch_downsample2x2(const uint8_t *d_src, int width, int height, si
 }
 
 // ---------------------------------------------------------------------------
+// A whole mip chain in ONE launch (the "single pass downsampler" scheme): the level-by-level path above costs one
+// launch per level, and below 256^2 a level is nothing but launch latency (2048^2 -> 1x1: eleven launches, ~30 us
+// of GPU time issued from C, ~115 us from Python, against 3.6 us of HBM traffic).  Here a 256-thread CTA takes a
+// 64x64 tile of the base and produces its 32x32 ... 1x1 reductions (levels 1-6): every thread reduces a 4x4 patch to
+// 2x2 (level 1) and 1x1 (level 2) in registers, levels 3-6 go through shared memory.  The CTA that finishes last
+// (a ticket in global memory) reduces the level-6 image -- one texel per tile -- down to 1x1, level by level.
+// Every level is the 2x2 box filter of the ROUNDED level before it, exactly as in the level-by-level path, so the
+// two produce the same bytes (tests/test_gpu_edges.py).  Requires width and height to be multiples of 64.
+// ---------------------------------------------------------------------------
+struct MipLevels {
+    uint8_t *ptr[kMaxMipLevels];          // level l+1 of the chain: (max(1, w >> (l+1))) x (max(1, h >> (l+1))), rows tightly packed
+    int32_t count;
+};
+
+__global__ void __launch_bounds__(256)
+mip_chain_fused_kernel(const uint8_t *__restrict__ base, size_t base_pitch, int width, int height, MipLevels lv, unsigned *ticket)
+{
+    __shared__ uint32_t s_a[16 * 16], s_b[8 * 8];
+    __shared__ bool s_last;
+    const uint32_t tiles_x = uint32_t(width) / 64u;
+    const uint32_t tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
+    const uint32_t t = threadIdx.x, tx = t & 15u, ty = t >> 4;
+    // ---- levels 1 and 2: a 4x4 patch of the base per thread (a warp reads 2 x 256 contiguous bytes per row) ----
+    const uint8_t *src = base + size_t(tile_y * 64u + ty * 4u) * base_pitch + size_t(tile_x * 64u + tx * 4u) * 4u;
+    const uint4 r0 = __ldcs(reinterpret_cast<const uint4 *>(src));
+    const uint4 r1 = __ldcs(reinterpret_cast<const uint4 *>(src + base_pitch));
+    const uint4 r2 = __ldcs(reinterpret_cast<const uint4 *>(src + 2 * base_pitch));
+    const uint4 r3 = __ldcs(reinterpret_cast<const uint4 *>(src + 3 * base_pitch));
+    const uint32_t a00 = box4(r0.x, r0.y, r1.x, r1.y), a01 = box4(r0.z, r0.w, r1.z, r1.w);
+    const uint32_t a10 = box4(r2.x, r2.y, r3.x, r3.y), a11 = box4(r2.z, r2.w, r3.z, r3.w);
+    {
+        const uint32_t w1 = uint32_t(width) >> 1;
+        uint8_t *d = lv.ptr[0] + (size_t(tile_y * 32u + ty * 2u) * w1 + (tile_x * 32u + tx * 2u)) * 4u;
+        *reinterpret_cast<uint2 *>(d) = make_uint2(a00, a01);
+        *reinterpret_cast<uint2 *>(d + size_t(w1) * 4u) = make_uint2(a10, a11);
+    }
+    const uint32_t l2 = box4(a00, a01, a10, a11);
+    if (lv.count > 1) {
+        const uint32_t w2 = uint32_t(width) >> 2;
+        reinterpret_cast<uint32_t *>(lv.ptr[1])[size_t(tile_y * 16u + ty) * w2 + (tile_x * 16u + tx)] = l2;
+    }
+    s_a[ty * 16u + tx] = l2;
+    __syncthreads();
+    // ---- levels 3..6 of the tile through shared memory: 8x8, 4x4, 2x2, 1x1 ----
+    uint32_t *cur = s_a, *nxt = s_b;
+#pragma unroll
+    for (int l = 3, n = 8; l <= 6; ++l, n >>= 1) {                 // n = side of level l inside the tile
+        if (t < uint32_t(n * n)) {
+            const uint32_t x = t % uint32_t(n), y = t / uint32_t(n), m = uint32_t(2 * n);
+            const uint32_t v = box4(cur[(2u * y) * m + 2u * x], cur[(2u * y) * m + 2u * x + 1u], cur[(2u * y + 1u) * m + 2u * x],
+                                    cur[(2u * y + 1u) * m + 2u * x + 1u]);
+            nxt[y * uint32_t(n) + x] = v;
+            if (l <= lv.count) {
+                const uint32_t wl = uint32_t(width) >> l;
+                reinterpret_cast<uint32_t *>(lv.ptr[l - 1])[size_t(tile_y * uint32_t(n) + y) * wl + (tile_x * uint32_t(n) + x)] = v;
+            }
+        }
+        __syncthreads();
+        uint32_t *tmp = cur; cur = nxt; nxt = tmp;
+    }
+    if (lv.count <= 6) return;
+    // ---- the last CTA to get here reduces the level-6 image (one texel per tile) to 1x1 ----
+    __threadfence();                                               // this CTA's level-6 texel is visible before its ticket
+    if (t == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    uint32_t w = uint32_t(width) >> 6, h = uint32_t(height) >> 6;
+    for (int l = 7; l <= lv.count; ++l) {
+        const uint32_t *in = reinterpret_cast<const uint32_t *>(lv.ptr[l - 2]);
+        uint32_t *out = reinterpret_cast<uint32_t *>(lv.ptr[l - 1]);
+        const uint32_t dx = w > 1u ? 1u : 0u, dy = h > 1u ? 1u : 0u;
+        const uint32_t ow = w > 1u ? w >> 1 : 1u, oh = h > 1u ? h >> 1 : 1u;
+        for (uint32_t i = t; i < ow * oh; i += 256u) {
+            const uint32_t y = i / ow, x = i - y * ow;
+            const uint32_t *p0 = in + size_t(y << dy) * w + (x << dx), *p1 = p0 + size_t(dy) * w;
+            out[i] = box4(__ldcg(p0), __ldcg(p0 + dx), __ldcg(p1), __ldcg(p1 + dx));     // L2, never a stale L1 line
+        }
+        __syncthreads();                                           // the level just written is read by other threads next
+        w = ow;
+        h = oh;
+    }
+    if (t == 0) *ticket = 0u;                                      // ready for the next launch on this stream
+}
+
+// Levels 1.. of the chain of a width x height image into `levels` (layout: mip_chain_layout in astc_capi.cu).
+cudaError_t launch_mip_chain(const uint8_t *d_base, int width, int height, size_t base_pitch, uint8_t *const *level_ptrs,
+                             const int *level_w, const int *level_h, int count, unsigned *d_ticket, cudaStream_t stream)
+{
+    if (count <= 0) return cudaSuccess;
+    const bool fused = width % 64 == 0 && height % 64 == 0 && base_pitch % 16u == 0 && reinterpret_cast<uintptr_t>(d_base) % 16u == 0 &&
+                       count <= kMaxMipLevels && d_ticket != nullptr;
+    if (fused) {
+        MipLevels lv{};
+        lv.count = count;
+        for (int l = 0; l < count; ++l) lv.ptr[l] = level_ptrs[l];
+        const unsigned ctas = unsigned(width / 64) * unsigned(height / 64);
+        mip_chain_fused_kernel<<<ctas, 256, 0, stream>>>(d_base, base_pitch, width, height, lv, d_ticket);
+        return cudaGetLastError();
+    }
+    // any size: one launch per level, issued back to back
+    const uint8_t *src = d_base;
+    size_t pitch = base_pitch;
+    int w = width, h = height;
+    for (int l = 0; l < count; ++l) {
+        const cudaError_t e = launch_downsample2x2(src, w, h, pitch, level_ptrs[l], size_t(level_w[l]) * 4u, stream);
+        if (e != cudaSuccess) return e;
+        src = level_ptrs[l];
+        w = level_w[l];
+        h = level_h[l];
+        pitch = size_t(w) * 4u;
+    }
+    return cudaSuccess;
+}
+
+// ---------------------------------------------------------------------------
 // The two hardware approximations the encoder's arithmetic is defined on (MUFU.RCP, MUFU.RSQ),
 // applied to an array: lets tests and tools/gen_mufu_tables.py compare the oracle's table-driven
 // emulation with the device, value by value.

@@ -52,6 +52,11 @@ cudaError_t launch_decode(const uint8_t *d_blocks, int width, int height, int di
                           cudaStream_t stream);
 cudaError_t launch_downsample2x2(const uint8_t *d_src, int width, int height, size_t src_pitch, uint8_t *d_dst, size_t dst_pitch,
                                  cudaStream_t stream);
+constexpr int kMaxMipLevels = 24;        // a 2^24-texel side is the .astc header's limit
+// levels 1..count of the mip chain of a width x height image; one fused launch when both sides are multiples of 64
+// (d_ticket: a zeroed device word the launch leaves zeroed), else one launch per level
+cudaError_t launch_mip_chain(const uint8_t *d_base, int width, int height, size_t base_pitch, uint8_t *const *level_ptrs,
+                             const int *level_w, const int *level_h, int count, unsigned *d_ticket, cudaStream_t stream);
 cudaError_t launch_mufu(int op, const float *d_x, float *d_y, size_t n, cudaStream_t stream);
 const float *host_srgb_lut();
 const float *host_unorm_lut();   // the c / 255.0f table the 4x4 kernels look up

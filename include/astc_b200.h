@@ -200,6 +200,19 @@ ASTC_B200_API int astc_b200_downsample2x2_device(const uint8_t *d_src, int width
                                                  size_t src_pitch_bytes, uint8_t *d_dst,
                                                  size_t dst_pitch_bytes, void *cuda_stream);
 
+/* The whole chain below a base image in ONE call: levels 1, 2, ... down to 1x1, each the 2x2 box filter of the level
+ * before it (the same bytes as repeated astc_b200_downsample2x2_device calls), written into one arena.
+ * astc_b200_mip_chain_layout tells where: level l+1 is widths[l] x heights[l], rows tightly packed, at byte offset
+ * offsets[l] (a multiple of 256); total_bytes includes a 256-byte scratch tail.  The arrays must hold 24 entries.
+ * When width and height are multiples of 64 (and the base is 16-byte aligned) the chain is ONE kernel launch (each
+ * CTA reduces a 64x64 tile through six levels, the last CTA to finish reduces the rest); otherwise one launch per
+ * level, issued back to back.  d_levels must be 256-byte aligned.  Async on the stream. */
+ASTC_B200_API int astc_b200_mip_chain_layout(int width, int height, int *levels, size_t *offsets,
+                                             int *widths, int *heights, size_t *total_bytes);
+ASTC_B200_API int astc_b200_mip_chain_device(const uint8_t *d_base, int width, int height,
+                                             size_t pitch_bytes, uint8_t *d_levels, size_t levels_bytes,
+                                             void *cuda_stream);
+
 /* ---- the hardware approximations the arithmetic is defined on ------------------------------ */
 /* y[i] = rcp.approx.ftz.f32(x[i]) (op 0) or rsqrt.approx.ftz.f32(x[i]) (op 1): what the reference's
  * `1.0f / x` (ASTC_Encode.hlsl:366) and normalize() (:103,332) execute on the hardware its golden

@@ -78,3 +78,18 @@ def test_argument_validation(native):
     assert L.astc_b200_downsample2x2_device(None, -1, 8, 32, None, 16, None) == -1
     assert L.astc_b200_downsample2x2_device(None, 0, 8, 32, None, 16, None) == 0       # empty image: nothing to do
     assert L.astc_b200_bise_encode_device(None, 65, 0, 1, None, None) == -1
+
+
+def test_mip_chain_layout(native):
+    """astc_b200_mip_chain_layout (host only): levels down to 1x1, 256-byte aligned offsets, a scratch tail."""
+    offs, ws, hs, total = native.mip_chain_layout(2048, 2048)
+    assert ws == hs == [1024 >> i for i in range(11)]
+    assert all(o % 256 == 0 for o in offs) and offs[0] == 0 and offs[1] == 1024 * 1024 * 4
+    assert total == offs[-1] + 256 + 256
+    assert native.mip_chain_layout(1, 1) == ([], [], [], 256)
+    offs, ws, hs, _ = native.mip_chain_layout(5, 3)
+    assert list(zip(ws, hs)) == [(2, 1), (1, 1)]
+    offs, ws, hs, _ = native.mip_chain_layout(64, 128)
+    assert list(zip(ws, hs)) == [(32, 64), (16, 32), (8, 16), (4, 8), (2, 4), (1, 2), (1, 1)]
+    n = __import__("ctypes").c_int()
+    assert native.lib().astc_b200_mip_chain_layout(0, 4, n, None, None, None, None) == -1

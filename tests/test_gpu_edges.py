@@ -290,3 +290,30 @@ def test_tapered_schedule_in_a_ragged_batch(native, dim):
     for s, o in zip(srcs, batch.outputs):
         assert torch.equal(o, native.encode_astc(s, opt)), tuple(s.shape)
     batch.close()
+
+
+@pytest.mark.parametrize("size", [(2048, 2048), (64, 64), (64, 128), (4096, 64), (192, 320), (1024, 576), (250, 187), (100, 64), (1, 9), (3, 3)], ids=str)
+def test_mip_chain_in_one_call(native, size):
+    """astc_b200_mip_chain_device: the whole chain in one call (ONE fused launch when both sides are multiples of 64)
+    must give the bytes of the level-by-level path; an arena can be reused (the fused kernel leaves its ticket zeroed)."""
+    import torch
+    from astc_encoder_b200 import synth
+    w, h = size
+    base = synth.synth_rgba(w, h, 31 + w + h, device="cuda")
+    want = native.mip_chain_by_level(base)
+    before = native.launch_count()
+    got = native.mip_chain(base)
+    launches = native.launch_count() - before
+    torch.cuda.synchronize()
+    assert [tuple(t.shape) for t in got] == [tuple(t.shape) for t in want]
+    for l, (a, b) in enumerate(zip(got, want)):
+        assert torch.equal(a, b), (size, l)
+    assert launches == (1 if (w % 64 == 0 and h % 64 == 0) else len(want) - 1)
+    _, _, _, total = native.mip_chain_layout(w, h)
+    arena = torch.full((total + 512,), 0xEE, dtype=torch.uint8, device="cuda")[:total + 256]     # garbage-filled, a little larger
+    for _ in range(3):
+        again = native.mip_chain(base, arena=arena)
+        torch.cuda.synchronize()
+        assert all(torch.equal(a, b) for a, b in zip(again, want))
+    strided = synth.synth_rgba(w + 8, h, 5, device="cuda")[:, 4:4 + w]                            # pitch > 4 * w, base 16-byte aligned
+    assert all(torch.equal(a, b) for a, b in zip(native.mip_chain(strided), native.mip_chain_by_level(strided)))
