@@ -39,7 +39,10 @@ def main() -> int:
         checked += len(want)
         # a mip-chain batch in one launch
         base = synth.synth_rgba(128, 128, 5).cuda()
-        chain = A.mip_chain(base)
+        chain = A.mip_chain(base)                                   # ONE fused launch (128 = 2 x 64): tiles, ticket, last-CTA tail
+        assert all(torch.equal(a, b) for a, b in zip(chain, A.mip_chain_by_level(base)))
+        odd = synth.synth_rgba(192, 320, 6).cuda()
+        assert all(torch.equal(a, b) for a, b in zip(A.mip_chain(odd), A.mip_chain_by_level(odd)))
         batch = A.Batch(chain, opt)
         outs = batch.encode()
         torch.cuda.synchronize()
@@ -54,6 +57,8 @@ def main() -> int:
         want = O.encode_image(himg, block_dim=dim, has_alpha=True)
         assert np.array_equal(got, want)
         checked += len(want)
+        big = synth.synth_rgba(1024, 520, 4).numpy()                # pageable and > 1 MiB: the staged pipeline (copy workers, pinned slots)
+        assert np.array_equal(A.encode_astc_host(big, opt), A.read_gpu(A.encode_astc(torch.from_numpy(big).cuda(), opt)))
         dec = A.decode_astc(torch.from_numpy(want).cuda(), 512, 384, dim).cpu().numpy()
         ref, nbad = O.decode_image(want, 512, 384, dim)
         assert nbad == 0 and np.array_equal(dec, ref)
