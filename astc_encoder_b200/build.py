@@ -23,7 +23,9 @@ SOURCES = ("astc_kernels.cu", "astc_capi.cu", "astc_context.cu", "image_io.cpp",
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "--expt-relaxed-constexpr", "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
-    "-Xcompiler", "-fPIC,-fvisibility=hidden,-ffp-contract=off", "-I", str(INCLUDE), "-I", str(CSRC),
+    # -fwrapv: the image decoders follow stb_image's int arithmetic, which wraps on corrupt input (e.g. the JPEG IDCT
+    # on garbage coefficients); wrapping is made defined behaviour instead of undefined
+    "-Xcompiler", "-fPIC,-fvisibility=hidden,-ffp-contract=off,-fwrapv", "-I", str(INCLUDE), "-I", str(CSRC),
 ]
 
 

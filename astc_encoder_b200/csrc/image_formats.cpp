@@ -553,7 +553,7 @@ bool decode_bmp(const std::vector<uint8_t> &file, Image &img)
     uint8_t *out = img.rgba.data();
     size_t z = 0;
     if (bpp < 16) {
-        if (psize == 0 || psize > 256) return fail("invalid");
+        if (psize <= 0 || psize > 256) return fail("invalid");       // (a data offset inside the header makes it negative)
         uint8_t pal[256][4];
         for (int i = 0; i < psize; ++i) {
             pal[i][2] = uint8_t(s.u8()); pal[i][1] = uint8_t(s.u8()); pal[i][0] = uint8_t(s.u8());

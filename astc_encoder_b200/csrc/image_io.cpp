@@ -211,6 +211,9 @@ bool decode_png(const std::vector<uint8_t> &file, Image &img)
     } else {
         raw_len = ((size_t(pi.w) * size_t(bpp_bits) + 7) / 8 + 1) * size_t(pi.h);
     }
+    // deflate expands at most ~1032 : 1, so a header that promises more pixels than the IDAT data can hold is
+    // rejected before anything of that size is allocated (a 30 000 x 30 000 IHDR on a 4 KB file)
+    if (raw_len / 1040u > idat.size() + 64u) return fail("not enough pixels");
     std::vector<uint8_t> raw(raw_len);
     uLongf got = uLongf(raw_len);
     const int zrc = uncompress(raw.data(), &got, idat.data(), uLong(idat.size()));
