@@ -94,3 +94,35 @@ def test_every_variant_whole_image_vs_oracle(native, oracle, dim, kw):
     assert got.shape == want.shape
     bad = int((got != want).any(axis=1).sum())
     assert bad == 0, f"{bad} of {len(want)} blocks differ"
+
+
+def test_texture_larger_than_4_gib(native):
+    """Byte offsets beyond 2^32 in one texture (34816 x 34816 RGBA8 = 4.5 GiB in, 1.1 GiB out; the .astc header allows
+    2^24 texels a side): the one-shot encode, the four bands of astc_b200_band and the fused mip chain of the same
+    texture must agree -- a 32-bit offset anywhere in the address arithmetic would not."""
+    import torch
+    from astc_encoder_b200 import synth
+    free, _ = torch.cuda.mem_get_info()
+    if free < 24 << 30:
+        pytest.skip("needs 24 GiB of free device memory")
+    side = 34816                                                       # 64 * 544
+    img = synth.synth_rgba(side, side, 4242, device="cuda", rows_per_chunk=512)
+    assert img.numel() > 1 << 32
+    for dim in (4, 6):
+        opt = native.encode_option(is4x4=dim == 4, is6x6=dim == 6)
+        whole = native.encode_astc(img, opt)
+        parts = []
+        for g in range(4):
+            y0, rows, off, nbytes = native.band(side, side, opt, 4, g)
+            parts.append(native.encode_astc(img[y0:y0 + rows], opt))
+            assert parts[-1].numel() == nbytes
+        torch.cuda.synchronize()
+        assert torch.equal(torch.cat(parts), whole), dim
+        del parts, whole
+    chain = native.mip_chain(img)                                      # one fused launch, 16 levels
+    assert tuple(chain[1].shape) == (side // 2, side // 2, 4)
+    assert torch.equal(chain[1], native.downsample2x2(img))
+    lvl = chain[1]
+    for nxt in chain[2:]:
+        assert torch.equal(nxt, native.downsample2x2(lvl))
+        lvl = nxt
