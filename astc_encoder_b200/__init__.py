@@ -120,6 +120,8 @@ _SIGNATURES = {
     "astc_b200_context_create": (C.c_int, [C.POINTER(C.c_void_p)]),
     "astc_b200_context_destroy": (None, [C.c_void_p]),
     "astc_b200_context_trim": (C.c_int, [C.c_void_p]),
+    "astc_b200_context_batch_encode_mip_chains_host": (C.c_int, [C.c_void_p, C.POINTER(_HostImage), C.c_int, C.POINTER(_Option)]),
+    "astc_b200_mip_chain_output_size": (C.c_int, [C.c_int, C.c_int, C.POINTER(_Option), C.POINTER(C.c_size_t), C.POINTER(C.c_int)]),
     "astc_b200_mip_chain_layout": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_size_t), C.POINTER(C.c_int),
                                              C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
     "astc_b200_mip_chain_device": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -331,6 +333,31 @@ class Context:
             res.append(dst)
             imgs[i] = _HostImage(im.ctypes.data, dst.ctypes.data, im.strides[0] if (h > 1 and im.size) else w * 4, w, h)
         _check(lib().astc_b200_context_batch_encode_host(self._h, imgs, len(images), C.byref(o)), "Context.batch_encode_host")
+        return res
+
+    def batch_encode_mip_chains_host(self, bases: Sequence[np.ndarray], option: encode_option) -> list:
+        """Whole mip chains from their BASE levels only (astc_b200_context_batch_encode_mip_chains_host): the bases are
+        uploaded, the levels below are generated and encoded on the device.  Returns, per base, the list of
+        (blocks, 16) uint8 arrays of its levels (base first; views into one buffer per chain)."""
+        o = option._abi()
+        imgs, res = (_HostImage * max(1, len(bases)))(), []
+        d = block_dim(option)
+        for i, im in enumerate(bases):
+            if im.dtype != np.uint8 or im.ndim != 3 or im.shape[2] != 4 or (im.size and (im.strides[2] != 1 or im.strides[1] != 4)):
+                raise ValueError("bases must be uint8 arrays of shape (H, W, 4) with packed texels")
+            h, w = im.shape[:2]
+            nbytes, levels = C.c_size_t(), C.c_int()
+            _check(lib().astc_b200_mip_chain_output_size(w, h, C.byref(o), C.byref(nbytes), C.byref(levels)), "mip_chain_output_size")
+            buf = np.empty(nbytes.value, dtype=np.uint8)
+            imgs[i] = _HostImage(im.ctypes.data, buf.ctypes.data, im.strides[0] if (h > 1 and im.size) else w * 4, w, h)
+            views, off, lw, lh = [], 0, w, h
+            for _ in range(levels.value):
+                n = ((lw + d - 1) // d) * ((lh + d - 1) // d) * BLOCK_BYTES
+                views.append(buf[off:off + n].reshape(-1, BLOCK_BYTES))
+                off += n
+                lw, lh = max(1, lw // 2), max(1, lh // 2)
+            res.append(views)
+        _check(lib().astc_b200_context_batch_encode_mip_chains_host(self._h, imgs, len(bases), C.byref(o)), "Context.batch_encode_mip_chains_host")
         return res
 
     def trim(self) -> None:

@@ -332,29 +332,10 @@ int astc_b200_downsample2x2_device(const uint8_t *d_src, int width, int height, 
     return ASTC_B200_OK;
 }
 
-// Layout of the levels below the base in one arena: level l+1 at offsets[l] (multiples of 256 bytes), rows tightly
-// packed (4 * widths[l] bytes), followed by a 256-byte scratch area for the fused kernel's ticket.
-static int mip_layout(int width, int height, size_t *offsets, int *widths, int *heights, size_t *total_bytes)
-{
-    int n = 0, w = width, h = height;
-    size_t off = 0;
-    while ((w > 1 || h > 1) && n < astc::kMaxMipLevels) {
-        w = w > 1 ? w / 2 : 1;
-        h = h > 1 ? h / 2 : 1;
-        if (offsets) offsets[n] = off;
-        if (widths) widths[n] = w;
-        if (heights) heights[n] = h;
-        off += (size_t(w) * size_t(h) * 4u + 255u) / 256u * 256u;
-        ++n;
-    }
-    if (total_bytes) *total_bytes = off + 256u;
-    return n;
-}
-
 int astc_b200_mip_chain_layout(int width, int height, int *levels, size_t *offsets, int *widths, int *heights, size_t *total_bytes)
 {
     if (width <= 0 || height <= 0 || !levels) return ASTC_B200_ERR_INVALID_ARGUMENT;
-    *levels = mip_layout(width, height, offsets, widths, heights, total_bytes);
+    *levels = astc_capi::mip_layout(width, height, offsets, widths, heights, total_bytes);
     return ASTC_B200_OK;
 }
 
@@ -365,7 +346,7 @@ int astc_b200_mip_chain_device(const uint8_t *d_base, int width, int height, siz
     if (width == 0 || height == 0) return ASTC_B200_OK;
     size_t offsets[astc::kMaxMipLevels], total = 0;
     int widths[astc::kMaxMipLevels], heights[astc::kMaxMipLevels];
-    const int n = mip_layout(width, height, offsets, widths, heights, &total);
+    const int n = astc_capi::mip_layout(width, height, offsets, widths, heights, &total);
     if (n == 0) return ASTC_B200_OK;                                  // a 1x1 base has no further levels
     if (!d_base || !d_levels || pitch_bytes < size_t(width) * 4u || pitch_bytes % 4u != 0 || levels_bytes < total ||
         reinterpret_cast<uintptr_t>(d_base) % 4u != 0 || reinterpret_cast<uintptr_t>(d_levels) % 256u != 0)

@@ -35,6 +35,28 @@ inline astc::ImageDesc make_desc(const uint8_t *rgba, uint8_t *blocks, size_t pi
     return d;
 }
 
+// Blocks of one texture.
+inline uint64_t block_count(int w, int h, int dim) { return uint64_t((w + dim - 1) / dim) * uint64_t((h + dim - 1) / dim); }
+
+// Layout of the levels below the base in one arena: level l+1 at offsets[l] (multiples of 256 bytes), rows tightly
+// packed (4 * widths[l] bytes), followed by a 256-byte scratch area for the fused kernel's ticket.
+inline int mip_layout(int width, int height, size_t *offsets, int *widths, int *heights, size_t *total_bytes)
+{
+    int n = 0, w = width, h = height;
+    size_t off = 0;
+    while ((w > 1 || h > 1) && n < astc::kMaxMipLevels) {
+        w = w > 1 ? w / 2 : 1;
+        h = h > 1 ? h / 2 : 1;
+        if (offsets) offsets[n] = off;
+        if (widths) widths[n] = w;
+        if (heights) heights[n] = h;
+        off += (size_t(w) * size_t(h) * 4u + 255u) / 256u * 256u;
+        ++n;
+    }
+    if (total_bytes) *total_bytes = off + 256u;
+    return n;
+}
+
 }  // namespace astc_capi
 
 #define CUDA_TRY(expr)                                                     \

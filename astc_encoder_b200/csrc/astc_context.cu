@@ -346,8 +346,14 @@ int astc_b200_encode_host(const uint8_t *h_rgba, int width, int height, size_t p
     return astc_b200_context_encode_host(ctx, h_rgba, width, height, pitch_bytes, opt, h_blocks);
 }
 
-int astc_b200_context_batch_encode_host(astc_b200_context *ctx, const astc_b200_host_image *images, int count,
-                                        const astc_b200_option *opt)
+}  // extern "C" (the shared implementation below is C++)
+
+namespace {
+
+// The body of both batch entry points.  `mips`: every image is the BASE of a mip chain -- only it is uploaded, the
+// levels below it are produced on the device (astc::launch_mip_chain: one fused launch per chain when both sides are
+// multiples of 64) and encoded by the same batch launch; im.h_blocks receives the blocks of all levels, base first.
+int batch_encode_host_impl(astc_b200_context *ctx, const astc_b200_host_image *images, int count, const astc_b200_option *opt, bool mips)
 {
     if (!opt || count < 0 || (count > 0 && !images) || opt->axis_method > 1) return ASTC_B200_ERR_INVALID_ARGUMENT;
     int rc = check_context(ctx);
@@ -360,9 +366,14 @@ int astc_b200_context_batch_encode_host(astc_b200_context *ctx, const astc_b200_
     // straight from / to the caller's buffer.  A group's slot mirrors the group's stretch of the device arena, so
     // every run of consecutive slot images is uploaded -- and every run of slot outputs downloaded -- with ONE copy.
     struct Item {
-        const astc_b200_host_image *im;
+        const uint8_t *h_src;            // nullptr: a mip level produced on the device
+        uint8_t *h_dst;
+        size_t src_pitch;
+        int w, h;
         size_t in_off, in_pitch, in_bytes, out_off, out_bytes;
-        bool via_in, via_out;
+        bool via_in, via_out, chain_head;
+        int levels;                      // chain_head: derived levels that follow
+        size_t mip_off;                  // chain_head: device offset of the chain's level arena (astc_capi::mip_layout)
         uint64_t blocks;
     };
     struct Group {
@@ -375,7 +386,7 @@ int astc_b200_context_batch_encode_host(astc_b200_context *ctx, const astc_b200_
     std::vector<astc::ImageDesc> table;
     size_t in_total = 0, out_total = 0, slot_in = 0, slot_out = 0;
     try {
-        items.reserve(size_t(count));
+        items.reserve(size_t(count) * (mips ? 13u : 1u));
         for (int i = 0; i < count; ++i) {
             const astc_b200_host_image &im = images[i];
             if (im.width < 0 || im.height < 0) return ASTC_B200_ERR_INVALID_ARGUMENT;
@@ -383,23 +394,55 @@ int astc_b200_context_batch_encode_host(astc_b200_context *ctx, const astc_b200_
             if (!im.h_rgba || !im.h_blocks || im.pitch_bytes < size_t(im.width) * 4u) return ASTC_B200_ERR_INVALID_ARGUMENT;
             if (too_many_blocks(im.width, im.height, d)) return ASTC_B200_ERR_UNSUPPORTED;
             Item it{};
-            it.im = &im;
+            it.h_src = im.h_rgba;
+            it.h_dst = im.h_blocks;
+            it.src_pitch = im.pitch_bytes;
+            it.w = im.width;
+            it.h = im.height;
             it.in_pitch = align_up(size_t(im.width) * 4u, 16);
             it.in_bytes = it.in_pitch * size_t(im.height);
             it.in_off = in_total;
             in_total += align_up(it.in_bytes, 256);
-            it.blocks = uint64_t((im.width + d - 1) / d) * uint64_t((im.height + d - 1) / d);
+            it.blocks = astc_capi::block_count(im.width, im.height, d);
             it.out_bytes = size_t(it.blocks) * 16u;
             it.out_off = out_total;
             out_total += it.out_bytes;
             // (images above a group's size never go through a slot: the slots stay bounded; the pointer query costs
             // about a microsecond, so it is skipped for images that take the slot anyway)
             it.via_in = it.in_bytes < kSmallImage || (it.in_bytes <= kGroupBytes && is_pageable(im.h_rgba));
-            it.via_out = it.out_bytes < kSmallImage / 4 || (it.in_bytes <= kGroupBytes && is_pageable(im.h_blocks));
-            items.push_back(it);
+            const bool pageable_out = it.in_bytes <= kGroupBytes && (mips || it.out_bytes >= kSmallImage / 4) && is_pageable(im.h_blocks);
+            it.via_out = it.out_bytes < kSmallImage / 4 || pageable_out;
+            it.chain_head = mips;
+            if (mips) {
+                size_t offs[astc::kMaxMipLevels], total = 0;
+                int ws[astc::kMaxMipLevels], hs[astc::kMaxMipLevels];
+                it.levels = astc_capi::mip_layout(im.width, im.height, offs, ws, hs, &total);
+                it.mip_off = in_total;
+                in_total += align_up(total, 256);
+                items.push_back(it);
+                uint8_t *dst = im.h_blocks + it.out_bytes;
+                for (int l = 0; l < it.levels; ++l) {
+                    Item lv{};
+                    lv.h_dst = dst;
+                    lv.w = ws[l];
+                    lv.h = hs[l];
+                    lv.in_pitch = size_t(ws[l]) * 4u;                  // the mip kernels pack rows tightly
+                    lv.in_bytes = lv.in_pitch * size_t(hs[l]);
+                    lv.in_off = it.mip_off + offs[l];
+                    lv.blocks = astc_capi::block_count(ws[l], hs[l], d);
+                    lv.out_bytes = size_t(lv.blocks) * 16u;
+                    lv.out_off = out_total;
+                    out_total += lv.out_bytes;
+                    lv.via_out = lv.out_bytes < kSmallImage / 4 || pageable_out;
+                    dst += lv.out_bytes;
+                    items.push_back(lv);
+                }
+            } else {
+                items.push_back(it);
+            }
         }
         if (items.empty()) return ASTC_B200_OK;
-        // groups of consecutive images, ~kGroupBytes of source each; block ids restart at 0 in every group
+        // groups of consecutive images (whole chains), ~kGroupBytes of uploaded source each; block ids restart at 0 in every group
         table.resize(items.size());
         for (size_t i = 0; i < items.size();) {
             Group g{};
@@ -407,15 +450,15 @@ int astc_b200_context_batch_encode_host(astc_b200_context *ctx, const astc_b200_
             g.in_off = items[i].in_off;
             g.out_off = items[i].out_off;
             size_t bytes = 0;
-            while (i < items.size() && (bytes == 0 || bytes + items[i].in_bytes <= kGroupBytes)) {
-                bytes += items[i].in_bytes;
+            while (i < items.size() && (bytes == 0 || items[i].h_src == nullptr || bytes + items[i].in_bytes <= kGroupBytes)) {
+                if (items[i].h_src) bytes += items[i].in_bytes;
                 ++i;
             }
             g.count = i - g.first;
             bool any_in = false, any_out = false;
             for (size_t k = g.first; k < i; ++k) {
                 const Item &it = items[k];
-                table[k] = make_desc(nullptr, nullptr, it.in_pitch, it.im->width, it.im->height, d, g.blocks);   // pointers filled in below
+                table[k] = make_desc(nullptr, nullptr, it.in_pitch, it.w, it.h, d, g.blocks);   // pointers filled in below
                 g.blocks += it.blocks;
                 g.out_bytes += it.out_bytes;
                 any_in |= it.via_in;
@@ -454,12 +497,12 @@ int astc_b200_context_batch_encode_host(astc_b200_context *ctx, const astc_b200_
         const uint8_t *slot = ctx->h_stage_out.ptr + size_t(s) * slot_out;
         for (size_t k = g.first; k < g.first + g.count; ++k) {
             const Item &it = items[k];
-            if (it.via_out) ctx->pool.copy_rows(it.im->h_blocks, it.out_bytes, slot + (it.out_off - g.out_off), it.out_bytes, it.out_bytes, 1);
+            if (it.via_out) ctx->pool.copy_rows(it.h_dst, it.out_bytes, slot + (it.out_off - g.out_off), it.out_bytes, it.out_bytes, 1);
         }
         return cudaSuccess;
     };
 
-    // ---- per group: slot fill + uploads, one launch, downloads; groups rotate over the streams and the slots ----
+    // ---- per group: slot fill + uploads, [mip chains,] one launch, downloads; groups rotate over the streams and the slots ----
     size_t retired = 0;
     for (size_t gi = 0; gi < groups.size() && err == cudaSuccess; ++gi) {
         const Group &g = groups[gi];
@@ -471,19 +514,20 @@ int astc_b200_context_batch_encode_host(astc_b200_context *ctx, const astc_b200_
         const size_t end = g.first + g.count;
         while (k < end && err == cudaSuccess) {
             const Item &it = items[k];
+            if (!it.h_src) { ++k; continue; }                  // a mip level: produced on the device below
             if (!it.via_in) {
-                err = upload_rows(ctx->d_in.ptr + it.in_off, it.in_pitch, it.im->h_rgba, it.im->pitch_bytes,
-                                  size_t(it.im->width) * 4u, size_t(it.im->height), st);
+                err = upload_rows(ctx->d_in.ptr + it.in_off, it.in_pitch, it.h_src, it.src_pitch, size_t(it.w) * 4u, size_t(it.h), st);
                 ++k;
                 continue;
             }
             // a run of slot images: consecutive in the batch, hence consecutive -- with the same 256-byte padding --
             // in the arena and in the slot: gathered by the host (workers for the large ones), uploaded with one copy
             size_t run_end = k;
-            for (; run_end < end && items[run_end].via_in; ++run_end) {
+            for (; run_end < end && items[run_end].h_src && items[run_end].via_in; ++run_end) {
                 const Item &sj = items[run_end];
-                ctx->pool.copy_rows(slot + (sj.in_off - g.in_off), sj.in_pitch, sj.im->h_rgba, sj.im->pitch_bytes,
-                                    size_t(sj.im->width) * 4u, size_t(sj.im->height), /*streaming=*/sj.in_bytes >= kSmallImage);
+                ctx->pool.copy_rows(slot + (sj.in_off - g.in_off), sj.in_pitch, sj.h_src, sj.src_pitch, size_t(sj.w) * 4u, size_t(sj.h),
+                                    /*streaming=*/sj.in_bytes >= kSmallImage);
+                if (sj.chain_head) { ++run_end; break; }       // its level arena follows in the device arena: the run ends here
             }
             const Item &last = items[run_end - 1];
             err = cudaMemcpyAsync(ctx->d_in.ptr + it.in_off, slot + (it.in_off - g.in_off), last.in_off + last.in_bytes - it.in_off,
@@ -491,6 +535,28 @@ int astc_b200_context_batch_encode_host(astc_b200_context *ctx, const astc_b200_
             k = run_end;
         }
         if (err != cudaSuccess) break;
+        if (mips) {
+            for (size_t c = g.first; c < end && err == cudaSuccess; ++c) {
+                const Item &it = items[c];
+                if (!it.chain_head || it.levels == 0) continue;
+                uint8_t *ptrs[astc::kMaxMipLevels];
+                int ws[astc::kMaxMipLevels], hs[astc::kMaxMipLevels];
+                for (int l = 0; l < it.levels; ++l) {
+                    const Item &lv = items[c + 1 + size_t(l)];
+                    ptrs[l] = ctx->d_in.ptr + lv.in_off;
+                    ws[l] = lv.w;
+                    hs[l] = lv.h;
+                }
+                size_t total = 0;
+                astc_capi::mip_layout(it.w, it.h, nullptr, nullptr, nullptr, &total);
+                unsigned *ticket = reinterpret_cast<unsigned *>(ctx->d_in.ptr + it.mip_off + total - 256u);
+                err = cudaMemsetAsync(ticket, 0, sizeof(unsigned), st);
+                if (err == cudaSuccess)
+                    err = astc::launch_mip_chain(ctx->d_in.ptr + it.in_off, it.w, it.h, it.in_pitch, ptrs, ws, hs, it.levels, ticket, st);
+                astc_capi::count_launch();
+            }
+            if (err != cudaSuccess) break;
+        }
         astc::EncodeParams p{};
         p.single = table[g.first];
         p.table = g.count > 1 ? ctx->d_table.ptr + g.first : nullptr;
@@ -505,7 +571,7 @@ int astc_b200_context_batch_encode_host(astc_b200_context *ctx, const astc_b200_
         while (k < end && err == cudaSuccess) {
             const Item &it = items[k];
             if (!it.via_out) {
-                err = cudaMemcpyAsync(it.im->h_blocks, ctx->d_out.ptr + it.out_off, it.out_bytes, cudaMemcpyDeviceToHost, st);
+                err = cudaMemcpyAsync(it.h_dst, ctx->d_out.ptr + it.out_off, it.out_bytes, cudaMemcpyDeviceToHost, st);
                 ++k;
                 continue;
             }
@@ -518,7 +584,36 @@ int astc_b200_context_batch_encode_host(astc_b200_context *ctx, const astc_b200_
     }
     for (size_t gi = retired; gi < groups.size() && err == cudaSuccess; ++gi) err = retire(gi);
     err = sync_all(ctx, err);
-    if (err != cudaSuccess) return cuda_fail(err, "astc_b200_context_batch_encode_host");
+    if (err != cudaSuccess) return cuda_fail(err, mips ? "astc_b200_context_batch_encode_mip_chains_host" : "astc_b200_context_batch_encode_host");
+    return ASTC_B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int astc_b200_context_batch_encode_host(astc_b200_context *ctx, const astc_b200_host_image *images, int count,
+                                        const astc_b200_option *opt)
+{
+    return batch_encode_host_impl(ctx, images, count, opt, /*mips=*/false);
+}
+
+int astc_b200_context_batch_encode_mip_chains_host(astc_b200_context *ctx, const astc_b200_host_image *bases, int count,
+                                                   const astc_b200_option *opt)
+{
+    return batch_encode_host_impl(ctx, bases, count, opt, /*mips=*/true);
+}
+
+int astc_b200_mip_chain_output_size(int width, int height, const astc_b200_option *opt, size_t *bytes, int *levels)
+{
+    if (width <= 0 || height <= 0 || !opt) return ASTC_B200_ERR_INVALID_ARGUMENT;
+    const int d = dim_of(opt);
+    int ws[astc::kMaxMipLevels], hs[astc::kMaxMipLevels];
+    const int n = astc_capi::mip_layout(width, height, nullptr, ws, hs, nullptr);
+    size_t total = size_t(astc_capi::block_count(width, height, d)) * 16u;
+    for (int l = 0; l < n; ++l) total += size_t(astc_capi::block_count(ws[l], hs[l], d)) * 16u;
+    if (bytes) *bytes = total;
+    if (levels) *levels = n + 1;
     return ASTC_B200_OK;
 }
 

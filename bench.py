@@ -592,6 +592,32 @@ def host_batch_e2e(torch, A, srcs, outs, opt, chains, chain_texels):
     launches = (A.launch_count() - l0) // 3
     ts.sort()
     same = all(bool(np.array_equal(d, o.cpu().numpy())) for d, o in list(zip(dsts, outs[:n]))[:: max(1, n // 200)])
+    # the same chains from their BASE levels only (astc_b200_context_batch_encode_mip_chains_host): the bases are
+    # uploaded (three quarters of the bytes), the levels below are generated AND encoded on the device; the output
+    # layout per chain -- base first, then level 1, 2, ... -- is the layout h_out already has
+    import ctypes as C
+    from astc_encoder_b200 import _HostImage
+    expect = h_out.clone()
+    h_out.zero_()
+    recs = (_HostImage * use)()
+    for c in range(use):
+        b = imgs[c * levels]
+        recs[c] = _HostImage(b.ctypes.data, dsts[c * levels].ctypes.data, b.strides[0], b.shape[1], b.shape[0])
+    o = opt._abi()
+    L = A.lib()
+    assert L.astc_b200_context_batch_encode_mip_chains_host(ctx._h, recs, use, C.byref(o)) == 0
+    bts = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        rc = L.astc_b200_context_batch_encode_mip_chains_host(ctx._h, recs, use, C.byref(o))
+        bts.append(time.perf_counter() - t0)
+        assert rc == 0
+    bts.sort()
+    bases_same = bool(torch.equal(h_out, expect))
+    from_bases = {"api": "astc_b200_context_batch_encode_mip_chains_host (C ABI): only the base levels are uploaded, pinned memory",
+                  "chains": use, "ms": round(bts[1] * 1e3, 2), "value": round(use * chain_texels / bts[1] / 1e6, 1), "unit": UNIT,
+                  "h2d_bytes": int(sum(int(imgs[c * levels].nbytes) for c in range(use))), "d2h_bytes": use * per_chain_out,
+                  "matches_all_levels_uploaded": bases_same}
     # the same call from PAGEABLE memory (plain numpy arrays -- what a caller without CUDA allocations holds): the
     # levels travel through the context's pinned slots, copied by its worker threads; 64 chains bound the host memory
     pg_use = min(use, 64)
@@ -611,7 +637,7 @@ def host_batch_e2e(torch, A, srcs, outs, opt, chains, chain_texels):
     return {"api": "astc_b200_context_batch_encode_host (C ABI), every level in pinned host memory", "chains": use, "textures": n,
             "ms": round(ts[1] * 1e3, 2), "value": round(use * chain_texels / ts[1] / 1e6, 1), "unit": UNIT,
             "h2d_bytes": use * per_chain_in, "d2h_bytes": use * per_chain_out, "launches_per_call": int(launches),
-            "matches_device_batch": same,
+            "matches_device_batch": same, "from_bases": from_bases,
             "pageable": {"chains": pg_use, "ms": round(pts[1] * 1e3, 2), "value": round(pg_use * chain_texels / pts[1] / 1e6, 1),
                          "unit": UNIT, "matches_pinned": pg_same,
                          "note": "sources and outputs in pageable numpy memory, staged through pinned slots by the context's copy workers"}}

@@ -153,6 +153,17 @@ ASTC_B200_API int astc_b200_context_batch_encode_host(astc_b200_context *ctx,
                                                       const astc_b200_host_image *images, int count,
                                                       const astc_b200_option *opt);
 
+/* The same for mip chains of which only the BASE levels exist on the host: each image is a base; it alone is uploaded,
+ * the levels below it (down to 1x1, astc_b200_mip_chain_device's box filter) are produced on the device and encoded by
+ * the same launch.  h_blocks receives the blocks of ALL levels, base first then level 1, 2, ...:
+ * astc_b200_mip_chain_output_size bytes (`levels` counts the base).  Three quarters of the upload of a chain whose
+ * levels were made on the host. */
+ASTC_B200_API int astc_b200_context_batch_encode_mip_chains_host(astc_b200_context *ctx,
+                                                                 const astc_b200_host_image *bases, int count,
+                                                                 const astc_b200_option *opt);
+ASTC_B200_API int astc_b200_mip_chain_output_size(int width, int height, const astc_b200_option *opt,
+                                                  size_t *bytes, int *levels);
+
 /* Many textures (mip chains) in ONE launch over a prefix-summed block table.
  * create() uploads the table; encode() is asynchronous and reusable.       */
 ASTC_B200_API int astc_b200_batch_create(const astc_b200_image *images, int count,

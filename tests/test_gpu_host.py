@@ -150,3 +150,34 @@ def test_staged_pipeline_for_pageable_memory(native, dim):
     ctx.encode_host(src.numpy(), opt, out=out_pin.numpy())
     assert np.array_equal(out_pin.numpy(), want)
     ctx.close()
+
+
+@pytest.mark.parametrize("dim,kw", [(4, dict()), (6, dict(has_alpha=True, srgb=True)), (4, dict(is_normal_map=True))], ids=str)
+def test_batch_encode_mip_chains_from_bases(native, dim, kw):
+    """astc_b200_context_batch_encode_mip_chains_host: only the bases travel to the device; every level's blocks must
+    equal the per-level encode of the chain made by mip_chain (fused launch for multiples of 64, per-level otherwise),
+    for pinned and pageable bases, several groups, odd sizes and a 1x1 base."""
+    import torch
+    from astc_encoder_b200 import synth
+    opt = native.encode_option(is4x4=dim == 4, is6x6=dim == 6, **kw)
+    gen = synth.synth_normal if kw.get("is_normal_map") else synth.synth_rgba
+    sizes = [(2048, 2048), (1024, 512), (250, 187), (64, 64), (1, 1), (4096, 2048), (2048, 2048), (3, 40), (4096, 4096), (128, 1024)]
+    bases = []
+    for i, (w, h) in enumerate(sizes):
+        t = gen(w, h, 300 + i)
+        if i % 3 == 1:
+            p = torch.empty(t.shape, dtype=torch.uint8, pin_memory=True)
+            p.copy_(t)
+            bases.append(p.numpy())
+        else:
+            bases.append(t.numpy())
+    ctx = native.Context()
+    for rep in range(2):                                                # the second call reuses workspace, slots and tickets
+        got = ctx.batch_encode_mip_chains_host(bases, opt)
+        for b, levels in zip(bases, got):
+            chain = native.mip_chain(torch.from_numpy(np.ascontiguousarray(b)).cuda())
+            assert len(levels) == len(chain), b.shape
+            for lv, blocks in zip(chain, levels):
+                assert np.array_equal(blocks, native.read_gpu(native.encode_astc(lv, opt))), (b.shape, tuple(lv.shape), rep)
+    assert ctx.batch_encode_mip_chains_host([], opt) == []
+    ctx.close()
