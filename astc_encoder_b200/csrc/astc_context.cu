@@ -32,7 +32,10 @@ namespace {
 
 constexpr int kStreams = 3;
 constexpr size_t kSmallImage = 256u << 10;        // sources below this travel through pinned staging (one memcpy beats one cudaMemcpyAsync call)
-constexpr size_t kGroupBytes = 64u << 20;         // source bytes per upload / launch / download group of a batch
+#ifndef ASTC_GROUP_MIB
+#define ASTC_GROUP_MIB 64
+#endif
+constexpr size_t kGroupBytes = size_t(ASTC_GROUP_MIB) << 20;   // source bytes per upload / launch / download group of a batch
 constexpr size_t kStagedMin = 1u << 20;           // pageable textures from this size on go through the staged pipeline below
 constexpr size_t kStagedBand = 4u << 20;          // source bytes per staged band (one pinned slot per stream)
 
