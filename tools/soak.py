@@ -55,7 +55,20 @@ def main():
         n = int(rng.integers(1, 5))
         imgs = [content(rng, int(rng.integers(1, 400)), int(rng.integers(1, 400))) for _ in range(n)]
         want = [O.encode_image(i, **okw) for i in imgs]
-        dev = [torch.from_numpy(i).cuda() for i in imgs]
+        # half of the textures are strided sub-views of a larger surface (pitch > 4 * width, base at an arbitrary texel),
+        # on the host and on the device
+        dev = []
+        for k in range(n):
+            if rng.random() < 0.5:
+                h, w = imgs[k].shape[:2]
+                ox, px = int(rng.integers(0, 9)), int(rng.integers(0, 9))
+                big = rng.integers(0, 256, (h, w + ox + px, 4), dtype=np.uint8)
+                big[:, ox:ox + w] = imgs[k]
+                imgs[k] = big[:, ox:ox + w]
+                dev.append(torch.from_numpy(big).cuda()[:, ox:ox + w])
+            else:
+                imgs[k] = np.ascontiguousarray(imgs[k])
+                dev.append(torch.from_numpy(imgs[k]).cuda())
         for i, d, w in zip(imgs, dev, want):
             got = A.read_gpu(A.encode_astc(d, opt))
             assert np.array_equal(got, w), ("single", c, dim, kw, i.shape)
