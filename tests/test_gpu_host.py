@@ -181,3 +181,30 @@ def test_batch_encode_mip_chains_from_bases(native, dim, kw):
                 assert np.array_equal(blocks, native.read_gpu(native.encode_astc(lv, opt))), (b.shape, tuple(lv.shape), rep)
     assert ctx.batch_encode_mip_chains_host([], opt) == []
     ctx.close()
+
+
+def test_batch_encode_host_levels_back_to_back_in_one_buffer(native):
+    """Levels that lie back to back in the caller's memory (a chain loaded from one file) are uploaded as ONE copy where
+    they are contiguous in the device arena too (sizes that are multiples of 256 bytes): same bytes as separate arrays,
+    from pinned and from pageable memory, with an odd-sized stranger in the middle."""
+    import torch
+    from astc_encoder_b200 import synth
+    opt = native.encode_option(has_alpha=True)
+    chains = [[t.cpu().numpy() for t in native.mip_chain(synth.synth_rgba(s, s, 40 + i).cuda())] for i, s in enumerate((1024, 2048, 512))]
+    odd = synth.synth_rgba(250, 187, 9).numpy()
+    flat = [lv for ch in chains[:2] for lv in ch] + [odd] + chains[2]
+    total = sum(lv.nbytes for lv in flat)
+    for pinned in (True, False):
+        buf = torch.empty(total, dtype=torch.uint8, pin_memory=pinned).numpy()
+        views, off = [], 0
+        for lv in flat:
+            v = buf[off:off + lv.nbytes].reshape(lv.shape)
+            v[...] = lv
+            views.append(v)
+            off += lv.nbytes
+        ctx = native.Context()
+        got = ctx.batch_encode_host(views, opt)
+        want = ctx.batch_encode_host(flat, opt)                           # separate arrays: nothing to merge
+        assert all(np.array_equal(a, b) for a, b in zip(got, want))
+        assert np.array_equal(got[0], _device_encode(native, flat[0], opt))
+        ctx.close()
