@@ -5,7 +5,7 @@
 //                                        astc_encode.h:87-194, astc_save.h:34-50) for ONE texture
 //   astc_b200_context_batch_encode_host  the same for MANY textures (mip chains): pinned staging for the
 //                                        small levels, banded uploads for the large ones, one kernel
-//                                        launch per group of ~64 MiB over a prefix-summed block table
+//                                        launch per group of ~32 MiB over a prefix-summed block table
 //
 // The reference creates its device objects once per process (main.cpp:199-209) and its texture / UAV
 // per encode; here the per-call objects are gone too: nothing is created or destroyed on the hot path
@@ -33,7 +33,7 @@ namespace {
 constexpr int kStreams = 3;
 constexpr size_t kSmallImage = 256u << 10;        // sources below this travel through pinned staging (one memcpy beats one cudaMemcpyAsync call)
 #ifndef ASTC_GROUP_MIB
-#define ASTC_GROUP_MIB 64
+#define ASTC_GROUP_MIB 32
 #endif
 constexpr size_t kGroupBytes = size_t(ASTC_GROUP_MIB) << 20;   // source bytes per upload / launch / download group of a batch
 constexpr size_t kStagedMin = 1u << 20;           // pageable textures from this size on go through the staged pipeline below

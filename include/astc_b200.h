@@ -147,7 +147,7 @@ typedef struct astc_b200_host_image {
     int32_t width, height;
 } astc_b200_host_image;
 /* Upload + encode + read back MANY textures (e.g. whole mip chains) in one synchronous call: levels under
- * 256 KiB are gathered through pinned staging, larger ones copied directly, ~64 MiB of source per
+ * 256 KiB are gathered through pinned staging, larger ones copied directly, ~32 MiB of source per
  * upload / launch / download group, groups pipelined over the context's streams. */
 ASTC_B200_API int astc_b200_context_batch_encode_host(astc_b200_context *ctx,
                                                       const astc_b200_host_image *images, int count,
