@@ -208,3 +208,42 @@ def test_batch_encode_host_levels_back_to_back_in_one_buffer(native):
         assert all(np.array_equal(a, b) for a, b in zip(got, want))
         assert np.array_equal(got[0], _device_encode(native, flat[0], opt))
         ctx.close()
+
+
+def test_contexts_are_independent_across_host_threads(native):
+    """re-entrant per (device, stream), no global mutable state.  Six host threads, each with its own context
+    (plus the thread-local default one), encode different textures concurrently -- pinned-free pageable sources, so the
+    copy workers of six pools run at the same time too; every result must equal the single-threaded one."""
+    import threading
+    from astc_encoder_b200 import synth
+    opts = [native.encode_option(), native.encode_option(is6x6=True, has_alpha=True, srgb=True), native.encode_option(is_normal_map=True)]
+    jobs = []
+    for i in range(6):
+        w, h = 700 + 131 * i, 900 - 77 * i
+        img = (synth.synth_normal if i % 3 == 2 else synth.synth_rgba)(w, h, 800 + i).numpy()
+        jobs.append((img, opts[i % 3]))
+    want = [_device_encode(native, img, opt) for img, opt in jobs]
+    errors = []
+
+    def work(k):
+        try:
+            img, opt = jobs[k]
+            ctx = native.Context()
+            for rep in range(8):
+                if not np.array_equal(ctx.encode_host(img, opt), want[k]):
+                    errors.append(("context", k, rep))
+                if not np.array_equal(native.encode_astc_host(img, opt), want[k]):
+                    errors.append(("default context", k, rep))
+                outs = ctx.batch_encode_host([img, img[: img.shape[0] // 2]], opt)
+                if not np.array_equal(outs[0], want[k]):
+                    errors.append(("batch", k, rep))
+            ctx.close()
+        except Exception as e:                                         # noqa: BLE001
+            errors.append((k, repr(e)))
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(len(jobs))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:5]
