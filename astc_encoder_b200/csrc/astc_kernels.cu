@@ -568,14 +568,24 @@ encode6x6_kernel(const EncodeParams p)
 // (4x4, 16384^2: 0.87 ms at 1 pass, 0.78 at 2, 0.75 at 4, 0.736 at 8), but the grid should keep about
 // three waves of resident CTAs or the last partial wave idles the SMs (4096^2 is best at 4 passes).
 // The 6x6 kernel has no prefetch to amortise and is best at 1-3 passes (measured on 8192^2).
+// SMs of the current device, asked once per (host thread, device).
+static int sm_count_of_current_device()
+{
+    static thread_local int cached_device = -1, cached_count = 148;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev != cached_device) {
+        int n = 148;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
+        cached_device = dev;
+        cached_count = n;
+    }
+    return cached_count;
+}
+
 static int choose_passes(uint64_t total_blocks, int threads, int ctas_per_sm, int max_passes)
 {
-    static thread_local int sm_count = 0;
-    if (sm_count == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-            sm_count = 148;
-    }
+    const int sm_count = sm_count_of_current_device();
 #ifdef ASTC_TUNING_HOOKS
     // experiment builds only (tools/variants.py build hooks=ASTC_TUNING_HOOKS): never compiled into the product library
     const char *force = getenv("ASTC_B200_PASSES");
@@ -593,9 +603,7 @@ static int choose_passes(uint64_t total_blocks, int threads, int ctas_per_sm, in
 #endif
 static uint64_t plan_schedule(EncodeParams &p, int threads, int ctas_per_sm)
 {
-    int sm_count = 148, dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sm_count = 148;
-    return plan_tapered(p, threads, uint64_t(sm_count) * uint64_t(ctas_per_sm), ASTC_TAPER != 0);
+    return plan_tapered(p, threads, uint64_t(sm_count_of_current_device()) * uint64_t(ctas_per_sm), ASTC_TAPER != 0);
 }
 
 template <typename K>
@@ -884,13 +892,7 @@ cudaError_t launch_downsample2x2(const uint8_t *d_src, int width, int height, si
                                  cudaStream_t stream)
 {
     const uint32_t ow = uint32_t(width > 1 ? width / 2 : 1), oh = uint32_t(height > 1 ? height / 2 : 1);
-    static thread_local int sm_count = 0;
-    if (sm_count == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-            sm_count = 148;
-    }
-    const uint64_t max_ctas = uint64_t(sm_count) * 8u * 4u;                   // 8 resident CTAs of 256 threads per SM, four waves
+    const uint64_t max_ctas = uint64_t(sm_count_of_current_device()) * 8u * 4u;                   // 8 resident CTAs of 256 threads per SM, four waves
     const bool vec = width > 1 && height > 1 && ow % 4u == 0 && src_pitch % 16u == 0 && dst_pitch % 16u == 0 &&
                      reinterpret_cast<uintptr_t>(d_src) % 16u == 0 && reinterpret_cast<uintptr_t>(d_dst) % 16u == 0;
     if (vec) {
