@@ -317,3 +317,44 @@ def test_mip_chain_in_one_call(native, size):
         assert all(torch.equal(a, b) for a, b in zip(again, want))
     strided = synth.synth_rgba(w + 8, h, 5, device="cuda")[:, 4:4 + w]                            # pitch > 4 * w, base 16-byte aligned
     assert all(torch.equal(a, b) for a, b in zip(native.mip_chain(strided), native.mip_chain_by_level(strided)))
+
+
+def test_encode_launches_can_be_captured_in_a_cuda_graph(native, oracle):
+    """The encode launches carry the programmatic-stream-serialization attribute; captured into a CUDA graph (three
+    launches back to back plus a mip chain and a batch) and replayed on new content they must still give the bytes of
+    eager launches."""
+    import torch
+    from astc_encoder_b200 import synth
+    opt4, opt6 = native.encode_option(has_alpha=True), native.encode_option(is6x6=True, srgb=True)
+    img = synth.synth_rgba(512, 384, 77, device="cuda")
+    out4, out6, out4b = native.encode_astc(img, opt4), native.encode_astc(img, opt6), native.encode_astc(img[:128], opt4)
+    _, _, _, total = native.mip_chain_layout(512, 384)
+    arena = torch.zeros(total, dtype=torch.uint8, device="cuda")
+    chain = native.mip_chain(img, arena=arena)
+    batch = native.Batch(chain, opt4)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        g.capture_begin()
+        native.encode_astc(img, opt4, out=out4, stream=s)
+        native.encode_astc(img, opt6, out=out6, stream=s)
+        native.encode_astc(img[:128], opt4, out=out4b, stream=s)
+        native.mip_chain(img, stream=s, arena=arena)
+        batch.encode(stream=s)
+        g.capture_end()
+    for seed in (5, 6):
+        img.copy_(synth.synth_rgba(512, 384, seed, device="cuda"))
+        for o in (out4, out6, out4b, *batch.outputs):
+            o.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        host = img.cpu().numpy()
+        assert np.array_equal(out4.cpu().numpy(), oracle.encode_image(host, block_dim=4, has_alpha=True))
+        assert np.array_equal(out6.cpu().numpy(), oracle.encode_image(host, block_dim=6, srgb=True))
+        assert np.array_equal(out4b.cpu().numpy(), oracle.encode_image(host[:128], block_dim=4, has_alpha=True))
+        want_chain = native.mip_chain_by_level(img)
+        for lv, o, w in zip(chain, batch.outputs, want_chain):
+            assert torch.equal(lv, w)
+            assert torch.equal(o, native.encode_astc(w, opt4))
+    batch.close()
