@@ -358,3 +358,33 @@ def test_encode_launches_can_be_captured_in_a_cuda_graph(native, oracle):
             assert torch.equal(lv, w)
             assert torch.equal(o, native.encode_astc(w, opt4))
     batch.close()
+
+
+@pytest.mark.parametrize("dim", [4, 6])
+@pytest.mark.parametrize("size", [(256, 192), (250, 187), (251, 187), (1024, 512), (5, 3)], ids=str)
+def test_decoder_fast_and_generic_paths_on_random_payloads(native, oracle, dim, size):
+    """decode_fast_kernel (aligned outputs: whole texel rows per store, packed weights, IDP4A interpolation) and the
+    generic decode_kernel (any alignment) against the oracle decoder, on blocks with the encoder's two headers but
+    RANDOM endpoint and weight bits: every trit code incl. the non-canonical ones, endpoint orders that need blue
+    contraction, ragged edges.  (250 / 251 texel rows are not 16- / 8-byte multiples: the generic path.)"""
+    import torch
+    from astc_encoder_b200 import synth
+    w, h = size
+    rng = np.random.default_rng(w * 7 + h + dim)
+    img = synth.synth_rgba(w, h, 12).cuda()
+    for kw in (dict(has_alpha=True), dict()):
+        opt = native.encode_option(is4x4=dim == 4, is6x6=dim == 6, **kw)
+        blocks = native.encode_astc(img, opt).cpu().numpy()
+        dec = native.decode_astc(torch.from_numpy(blocks).cuda(), w, h, dim).cpu().numpy()
+        ref, bad = oracle.decode_image(blocks, w, h, dim)
+        assert bad == 0 and np.array_equal(dec, ref), ("encoded", size, kw)
+        noise = rng.integers(0, 256, blocks.shape, dtype=np.uint8)
+        noise[:, 0] = blocks[:, 0]                                   # keep mode, partition count, CEM (bits 0..16)
+        noise[:, 1] = blocks[:, 1]
+        noise[:, 2] = (noise[:, 2] & 0xFE) | (blocks[:, 2] & 0x01)
+        dec = native.decode_astc(torch.from_numpy(noise).cuda(), w, h, dim).cpu().numpy()
+        ref, bad = oracle.decode_image(noise, w, h, dim)
+        assert bad == 0 and np.array_equal(dec, ref), ("random payload", size, kw)
+    garbage = rng.integers(0, 256, blocks.shape, dtype=np.uint8)      # anything else: decoded or the error colour, never a fault
+    native.decode_astc(torch.from_numpy(garbage).cuda(), w, h, dim)
+    torch.cuda.synchronize()
