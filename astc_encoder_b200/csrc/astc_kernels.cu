@@ -431,16 +431,31 @@ encode4x4_kernel(const EncodeParams p)
 #define ASTC_THREADS_6X6 128
 #endif
 constexpr int kThreads6x6 = ASTC_THREADS_6X6;
-constexpr int kPark6x6 = 26;
+// How many of a block's 36 texels are parked in shared memory (the rest stay in registers), per variant.  Every parked
+// texel costs one 16-byte store and three 16-byte loads per block, and the 6x6 kernels run at ~3/4 of the SM's
+// shared-memory bandwidth (40 M wavefronts per 8192^2 launch, 0.74 per clock and SM) -- so, registers permitting, fewer is
+// faster.  With the texel-major weight pass there is room for more register texels than the 10 of round 1
+// (measured, round 2af: profiles/r2af_ab_6x6_park.txt).
+#ifndef ASTC_6X6_PARK_LINEAR
+#define ASTC_6X6_PARK_LINEAR 24
+#endif
+#ifndef ASTC_6X6_PARK_SRGB
+#define ASTC_6X6_PARK_SRGB 18
+#endif
+#ifndef ASTC_6X6_PARK_NORMAL
+#define ASTC_6X6_PARK_NORMAL 16
+#endif
+template <bool NORMAL, bool SRGB>
+constexpr int park6x6() { return NORMAL ? ASTC_6X6_PARK_NORMAL : SRGB ? ASTC_6X6_PARK_SRGB : ASTC_6X6_PARK_LINEAR; }
 #ifndef ASTC_EXTRA_SMEM_6X6
 #define ASTC_EXTRA_SMEM_6X6 0            // occupancy experiments only (tools/variants.py)
 #endif
 
-template <bool NORMAL>
+template <bool NORMAL, int kPark6x6>
 struct Texels6x6 {
     using Slot = typename std::conditional<NORMAL, float2, float4>::type;
     static constexpr bool kStreamed = true;
-    static constexpr int kLoopRows = 4;                   // rows 0..3 (24 texels) are wholly in shared memory
+    static constexpr int kLoopRows = kPark6x6 / 6 < 4 ? kPark6x6 / 6 : 4;   // the texel rows that lie wholly in shared memory (rows 0..3 with 26 parked)
     Slot *col;                                            // &smem[threadIdx.x], stride kThreads6x6
     Texel reg[36 - kPark6x6];
     __device__ __forceinline__ void put(int k, const Texel &t)
@@ -468,19 +483,24 @@ struct Texels6x6 {
     __device__ __forceinline__ void sched_fence() const { __syncwarp(); }
 };
 
-template <bool NORMAL>
+template <bool NORMAL, bool SRGB>
 constexpr size_t smem6x6()
 {
-    return size_t(kPark6x6) * kThreads6x6 * sizeof(typename Texels6x6<NORMAL>::Slot) + sizeof(dev::SharedTables) + ASTC_EXTRA_SMEM_6X6;
+    return size_t(park6x6<NORMAL, SRGB>()) * kThreads6x6 * sizeof(typename Texels6x6<NORMAL, park6x6<NORMAL, SRGB>()>::Slot) +
+           sizeof(dev::SharedTables) + ASTC_EXTRA_SMEM_6X6;
 }
+#ifndef ASTC_6X6_CTAS
+#define ASTC_6X6_CTAS 4
+#endif
 template <bool NORMAL>
-constexpr int ctas6x6() { return NORMAL ? 6 : 4; }
+constexpr int ctas6x6() { return NORMAL ? 6 : ASTC_6X6_CTAS; }
 
 template <bool ALPHA, bool NORMAL, bool SRGB, bool BATCH, bool ACCUM>
 __global__ void __launch_bounds__(kThreads6x6, ctas6x6<NORMAL>())
 encode6x6_kernel(const EncodeParams p)
 {
-    using TX = Texels6x6<NORMAL>;
+    constexpr int kPark6x6 = park6x6<NORMAL, SRGB>();
+    using TX = Texels6x6<NORMAL, kPark6x6>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typename TX::Slot *s_tex = reinterpret_cast<typename TX::Slot *>(smem_raw);         // [kPark6x6][kThreads6x6]
     dev::SharedTables &st = *reinterpret_cast<dev::SharedTables *>(s_tex + kPark6x6 * kThreads6x6);
@@ -637,7 +657,7 @@ static cudaError_t launch_variant(int dim, EncodeParams p, cudaStream_t stream)
         return launch_pdl(encode4x4_kernel<ALPHA, NORMAL, SRGB, BATCH, ACCUM>, unsigned(ctas), kThreads4x4, 0, stream, p);
     } else {
         auto kern = encode6x6_kernel<ALPHA, NORMAL, SRGB, BATCH, ACCUM>;
-        constexpr size_t kSmem6x6 = smem6x6<NORMAL>();
+        constexpr size_t kSmem6x6 = smem6x6<NORMAL, SRGB>();
         constexpr int kCtas6x6 = ctas6x6<NORMAL>();
         p.passes = choose_passes(p.total_blocks, kThreads6x6, kCtas6x6, 2);
         const uint64_t ctas = plan_schedule(p, kThreads6x6, kCtas6x6);
